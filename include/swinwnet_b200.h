@@ -1,0 +1,102 @@
+/* C ABI of libswinwnet_b200.so — the sm_100a kernels behind the SwinWNet forward hot path.
+ *
+ * The reference (popoff4rtem/SwinWNet-...) is pure Python/PyTorch and has NO plugin / FFI layer: its
+ * operator surface for this path is the nn.Module method set SwinWNet.segment_1 / upscale / segment_2
+ * (/root/reference/SwinWNet.py:886-957) plus SwinUNet.forward (:574) and SwinUNetSR.forward (:740).
+ * The drop-in module in the package (model.py) keeps that surface and lowers every ATen op group the
+ * reference dispatches onto the entry points below, bound with ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer (tensor.data_ptr()), dense row-major, 16-byte aligned;
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous and CUDA-graph capturable;
+ *   - nothing is allocated internally; outputs/workspaces are caller-owned;
+ *   - return 0 on success, non-zero on error (1 = unsupported shape/argument, 2 = CUDA error);
+ *     swn_last_error() returns a thread-local message.  There is NO CPU fallback.
+ */
+#ifndef SWINWNET_B200_H
+#define SWINWNET_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SWN_ABI_VERSION 1
+
+/* A-operand prologues of swn_rowgemm */
+#define SWN_A_F32_LN 0   /* fp32 rows -> LayerNorm -> bf16          (norm1+qkv :242,:185; norm_q/kv+in_proj :779-782) */
+#define SWN_A_F32 1      /* fp32 rows -> bf16                       (PatchExpanding.expand :402; decoder linears :489) */
+#define SWN_A_BF16 2     /* bf16 rows                               (attention output -> proj :207 / out_proj :782)    */
+#define SWN_A_MERGE_LN 3 /* 2x2 gather [x00,x10,x01,x11] + LayerNorm (PatchMerging :295-312)                           */
+/* epilogues of swn_rowgemm */
+#define SWN_E_BF16 0   /* out_bf16 = acc + bias                                                                     */
+#define SWN_E_F32 1    /* out_f32 = alpha*(acc + bias) + residual      (proj+shortcut :277; q + gamma*attn :783)      */
+#define SWN_E_EXPAND 2 /* pixel-shuffle scatter + LayerNorm(C/2) + crop (PatchExpanding :404-410, crop_to_res :414)   */
+
+typedef struct swn_rowgemm_args {
+  const void* A; int32_t a_mode; int32_t M, K, lda;
+  const float* ln_w; const float* ln_b; float ln_eps;
+  int32_t gH, gW, gC, gHo, gWo;
+  const void* Wp;            /* packed bf16 weight tiles, see swn_rowgemm doc */
+  int32_t NT, nchunks, n_valid;
+  int32_t e_mode; const float* bias; void* out; int32_t ldo;
+  const float* res; int32_t ldres; const float* alpha;
+  int32_t xH, xW, xHs, xWs; const float* ln2_w; const float* ln2_b;
+} swn_rowgemm_args;
+
+const char* swn_last_error(void);
+int swn_abi_version(void);
+int swn_sizeof_rowgemm_args(void); /* lets FFI bindings verify their struct mirror */
+
+/* Tile configuration of the fused MLP for channel width C (the weight packer must use the same):
+ * HC = hidden-chunk width, TR = fc2 output rows per weight tile. */
+int swn_mlp_config(int C, int* HC, int* TR);
+
+/* out = epilogue(prologue(A)[M,K] * W[N,K]^T), N = nchunks*n_valid, on tcgen05 tensor cores.
+ * Wp: for chunk n, k-block kb (64 K-elements): a [NT x 64] bf16 tile in the UMMA K-major SWIZZLE_128B
+ * image (row r at r*128 B, 16-byte chunk c stored at chunk c ^ (r & 7)), rows >= n_valid and
+ * k >= K zero; tiles ordered (n, kb).  bias: nchunks*NT floats (padded). */
+int swn_rowgemm(const swn_rowgemm_args* args, void* stream);
+
+/* out[M,C] = x + fc2(GELU(fc1(LayerNorm(x))))   (SwinTransformerBlock MLP, SwinWNet.py:226-234,278).
+ * Wp = tile stream in consumption order, see packing.py::pack_mlp_weights; b2 padded to ceil16(C). */
+int swn_mlp(const float* x, float* out, int M, int C, const float* ln_w, const float* ln_b, float ln_eps,
+            const void* Wp, const float* b1, const float* b2, void* stream);
+
+/* 5x5 (shifted-)window attention core on token-ordered qkv (SwinWNet.py:86-149,183-206,246-272). */
+int swn_window_attention(const void* qkv_bf16, void* out_bf16, const float* qkv_bias, const float* rpb_table,
+                         int B, int H, int W, int C, int num_heads, int shift, void* stream);
+
+/* flash-style global cross attention core, heads of 64 or 128 channels (SwinWNet.py:782). */
+int swn_cross_attention(const void* q_bf16, const void* kv_bf16, void* out_bf16, int B, int Lq, int Lk, int C,
+                        int num_heads, void* stream);
+
+/* ScaleAwarePatchEmbed: 2x2 conv, stride 2*scale, dilation scale, + LayerNorm(48) (SwinWNet.py:53-82). */
+int swn_patch_embed(const float* x, const float* w, const float* b, const float* ln_w, const float* ln_b,
+                    float* out_tokens, int B, int Cin, int H, int W, int Ho, int Wo, int scale, void* stream);
+
+/* SegmentationHead: conv3x3(48->24)+GELU+conv1x1(24->1) -> lowres[B,Hq,Wq]; bilinear x`up`; crop
+ * (SwinWNet.py:507-531). */
+int swn_seg_head(const float* tokens, const float* w1, const float* b1, const float* w2, const float* b2,
+                 float* lowres, float* out, int B, int Hq, int Wq, int up, int Hout, int Wout, void* stream);
+
+/* UpscalingHead tail: conv3x3(12->12)+GELU+conv1x1(12->Cout), NCHW, cropped (SwinWNet.py:682-688,932). */
+int swn_recon_head(const float* tokens, const float* w1, const float* b1, const float* w2, const float* b2,
+                   float* out, int B, int Hh, int Wh, int Cout, int Hout, int Wout, void* stream);
+
+/* dst[r, 0:cols] = src[r, 0:cols]  (decoder skip concat, SwinWNet.py:483). */
+int swn_copy_cols(const float* src, int lds, float* dst, int ldd, long long rows, int cols, void* stream);
+
+/* ST pipeline glue (ST_Inference_Pipline.py:32-37,90-97,127-134): images2 = ensure_2ch(img) (optional),
+ * seg_map = sigmoid(seg), masked = images * seg_map, minmax[B*Cout][2] = per-image amin/amax (optional). */
+int swn_sigmoid_mask(const float* img, int Cimg, const float* seg, float* images2, float* seg_map, float* masked,
+                     float* minmax, int B, int Cout, int H, int W, void* stream);
+
+/* normalize_piecewise (inverse=0) / denormalize_piecewise (inverse=1) (ST_Inference_Pipline.py:39-67). */
+int swn_normalize(const float* x, const float* minmax, float* out, int BC, int H, int W, float threshold, float eps,
+                  int inverse, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,123 @@
+// extern "C" boundary of libswinwnet_b200.so (declared in include/swinwnet_b200.h).
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/swinwnet_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace swn {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+static void mlp_config(int C, int* HC, int* TR) {
+  const int C16 = (C + 15) & ~15, Hd = 4 * C, hbase = (C16 + 31) & ~31;
+  if (Hd % 128 == 0 && hbase + 256 <= 512) *HC = 128;
+  else if (Hd % 64 == 0) *HC = 64;
+  else *HC = Hd;
+  *TR = C16 <= 256 ? C16 : C16 / 2;
+}
+}  // namespace swn
+
+using namespace swn;
+
+extern "C" {
+
+const char* swn_last_error(void) { return g_err; }
+int swn_abi_version(void) { return SWN_ABI_VERSION; }
+int swn_sizeof_rowgemm_args(void) { return (int)sizeof(swn_rowgemm_args); }
+
+int swn_mlp_config(int C, int* HC, int* TR) {
+  SWN_CHECK(C >= 4 && C % 4 == 0 && C <= 384 && HC && TR, "mlp_config: unsupported C=%d", C);
+  mlp_config(C, HC, TR);
+  return 0;
+}
+
+int swn_rowgemm(const swn_rowgemm_args* a, void* stream) {
+  SWN_CHECK(a != nullptr, "rowgemm: null args");
+  RowGemmParams p{};
+  p.A = a->A; p.a_mode = a->a_mode; p.M = a->M; p.K = a->K; p.lda = a->lda;
+  p.ln_w = a->ln_w; p.ln_b = a->ln_b; p.ln_eps = a->ln_eps;
+  p.gH = a->gH; p.gW = a->gW; p.gC = a->gC; p.gHo = a->gHo; p.gWo = a->gWo;
+  p.Wp = reinterpret_cast<const __nv_bfloat16*>(a->Wp);
+  p.NT = a->NT; p.nchunks = a->nchunks; p.n_valid = a->n_valid;
+  p.e_mode = a->e_mode; p.bias = a->bias; p.out = a->out; p.ldo = a->ldo;
+  p.res = a->res; p.ldres = a->ldres; p.alpha = a->alpha;
+  p.xH = a->xH; p.xW = a->xW; p.xHs = a->xHs; p.xWs = a->xWs; p.ln2_w = a->ln2_w; p.ln2_b = a->ln2_b;
+  SWN_CHECK(p.A && p.Wp && p.out, "rowgemm: null pointer");
+  SWN_CHECK(p.a_mode >= 0 && p.a_mode <= 3 && p.e_mode >= 0 && p.e_mode <= 2, "rowgemm: bad mode");
+  if (p.a_mode == A_F32_LN || p.a_mode == A_MERGE_LN) SWN_CHECK(p.ln_w && p.ln_b, "rowgemm: LayerNorm params missing");
+  if (p.e_mode == E_EXPAND) SWN_CHECK(p.ln2_w && p.ln2_b && p.nchunks == 4, "rowgemm: expand needs 4 chunks + LN params");
+  return launch_rowgemm(p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int swn_mlp(const float* x, float* out, int M, int C, const float* ln_w, const float* ln_b, float ln_eps, const void* Wp,
+            const float* b1, const float* b2, void* stream) {
+  SWN_CHECK(x && out && ln_w && ln_b && Wp && b1 && b2, "mlp: null pointer");
+  SWN_CHECK(C >= 4 && C % 4 == 0 && C <= 384, "mlp: unsupported C=%d", C);
+  MlpParams p{};
+  p.x = x; p.out = out; p.M = M; p.C = C; p.ln_w = ln_w; p.ln_b = ln_b; p.ln_eps = ln_eps;
+  p.Wp = reinterpret_cast<const __nv_bfloat16*>(Wp); p.b1 = b1; p.b2 = b2;
+  mlp_config(C, &p.HC, &p.TR);
+  return launch_mlp(p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int swn_window_attention(const void* qkv, void* out, const float* qkv_bias, const float* rpb_table, int B, int H, int W,
+                         int C, int num_heads, int shift, void* stream) {
+  SWN_CHECK(qkv && out && qkv_bias && rpb_table, "window_attention: null pointer");
+  SWN_CHECK(B > 0 && H > 0 && W > 0 && C % 4 == 0 && num_heads > 0 && shift >= 0, "window_attention: bad sizes");
+  WinAttnParams p{reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), qkv_bias, rpb_table,
+                  B, H, W, C, num_heads, shift};
+  return launch_window_attn(p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int swn_cross_attention(const void* q, const void* kv, void* out, int B, int Lq, int Lk, int C, int num_heads,
+                        void* stream) {
+  SWN_CHECK(q && kv && out, "cross_attention: null pointer");
+  CrossAttnParams p{reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(kv),
+                    reinterpret_cast<__nv_bfloat16*>(out), B, Lq, Lk, C, num_heads};
+  return launch_cross_attn(p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int swn_patch_embed(const float* x, const float* w, const float* b, const float* ln_w, const float* ln_b, float* out,
+                    int B, int Cin, int H, int W, int Ho, int Wo, int scale, void* stream) {
+  SWN_CHECK(x && w && b && ln_w && ln_b && out, "patch_embed: null pointer");
+  return launch_patch_embed(x, w, b, ln_w, ln_b, out, B, Cin, H, W, Ho, Wo, scale, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int swn_seg_head(const float* tok, const float* w1, const float* b1, const float* w2, const float* b2, float* lowres,
+                 float* out, int B, int Hq, int Wq, int up, int Hout, int Wout, void* stream) {
+  SWN_CHECK(tok && w1 && b1 && w2 && b2 && lowres && out, "seg_head: null pointer");
+  SWN_CHECK(Hout <= Hq * up && Wout <= Wq * up, "seg_head: crop larger than upsampled map");
+  return launch_seg_head(tok, w1, b1, w2, b2, lowres, out, B, Hq, Wq, up, Hout, Wout, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int swn_recon_head(const float* tok, const float* w1, const float* b1, const float* w2, const float* b2, float* out,
+                   int B, int Hh, int Wh, int Cout, int Hout, int Wout, void* stream) {
+  SWN_CHECK(tok && w1 && b1 && w2 && b2 && out, "recon_head: null pointer");
+  return launch_recon_head(tok, w1, b1, w2, b2, out, B, Hh, Wh, Cout, Hout, Wout, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int swn_copy_cols(const float* src, int lds, float* dst, int ldd, long long rows, int cols, void* stream) {
+  SWN_CHECK(src && dst, "copy_cols: null pointer");
+  return launch_copy_cols(src, lds, dst, ldd, rows, cols, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int swn_sigmoid_mask(const float* img, int Cimg, const float* seg, float* images2, float* seg_map, float* masked,
+                     float* minmax, int B, int Cout, int H, int W, void* stream) {
+  SWN_CHECK(img && seg && masked, "sigmoid_mask: null pointer");
+  return launch_sigmoid_mask(img, Cimg, seg, images2, seg_map, masked, minmax, B, Cout, H, W,
+                             reinterpret_cast<cudaStream_t>(stream));
+}
+
+int swn_normalize(const float* x, const float* minmax, float* out, int BC, int H, int W, float threshold, float eps,
+                  int inverse, void* stream) {
+  SWN_CHECK(x && minmax && out, "normalize: null pointer");
+  return launch_normalize(x, minmax, out, BC, H, W, threshold, eps, inverse, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

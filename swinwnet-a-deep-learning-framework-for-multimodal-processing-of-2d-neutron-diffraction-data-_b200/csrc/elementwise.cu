@@ -1,0 +1,319 @@
+// Bandwidth-bound kernels of the SwinWNet forward: ScaleAwarePatchEmbed (SwinWNet.py:53-82), the
+// SegmentationHead / UpscalingHead conv tails (SwinWNet.py:507-531, 682-688), skip-concat column copy
+// (SwinWNet.py:483) and the ST inference pipeline glue (ST_Inference_Pipline.py:32-67, 90-97, 127-134).
+// All are vectorised, coalesced CUDA-core kernels judged on achieved HBM GB/s.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace swn {
+
+// ---------------------------------------------------------------------------------------------
+// Patch embed: 2x2 conv with stride 2*s and dilation s (s=1: LR, s=2: HR), bias, LayerNorm(48).
+// One thread per token; results are staged through shared memory so the [tokens x 48] fp32 output is
+// written fully coalesced.
+// ---------------------------------------------------------------------------------------------
+constexpr int PE_E = 48, PE_THREADS = 128;
+
+__global__ void __launch_bounds__(PE_THREADS) patch_embed_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                  const float* __restrict__ bias,
+                                                                  const float* __restrict__ ln_w,
+                                                                  const float* __restrict__ ln_b, float* __restrict__ out,
+                                                                  int B, int Cin, int H, int W, int Ho, int Wo, int s) {
+  __shared__ float w_s[4 * 4 * PE_E];  // [Cin*4 taps][48], Cin <= 4
+  __shared__ float p_s[3 * PE_E];      // bias, ln_w, ln_b
+  __shared__ float o_s[PE_THREADS * (PE_E + 1)];
+  const int taps = Cin * 4;
+  for (int i = threadIdx.x; i < taps * PE_E; i += PE_THREADS) {
+    const int tap = i / PE_E, e = i % PE_E;  // w is [E][Cin][2][2] -> tap = c*4 + a*2 + b
+    w_s[i] = w[e * taps + tap];
+  }
+  for (int i = threadIdx.x; i < PE_E; i += PE_THREADS) {
+    p_s[i] = bias[i];
+    p_s[PE_E + i] = ln_w[i];
+    p_s[2 * PE_E + i] = ln_b[i];
+  }
+  __syncthreads();
+  const long long total = (long long)B * Ho * Wo;
+  const long long t0 = (long long)blockIdx.x * PE_THREADS;
+  const long long t = t0 + threadIdx.x;
+  if (t < total) {
+    const int b = (int)(t / ((long long)Ho * Wo));
+    const int rem = (int)(t - (long long)b * Ho * Wo);
+    const int i = rem / Wo, j = rem - i * Wo;
+    float acc[PE_E];
+#pragma unroll
+    for (int e = 0; e < PE_E; ++e) acc[e] = p_s[e];
+    for (int c = 0; c < Cin; ++c) {
+#pragma unroll
+      for (int ab = 0; ab < 4; ++ab) {
+        const int y = i * 2 * s + (ab >> 1) * s, xx = j * 2 * s + (ab & 1) * s;
+        const float v = (y < H && xx < W) ? __ldg(x + (((long long)b * Cin + c) * H + y) * W + xx) : 0.f;
+        const float* wr = w_s + (c * 4 + ab) * PE_E;
+#pragma unroll
+        for (int e = 0; e < PE_E; ++e) acc[e] = fmaf(v, wr[e], acc[e]);
+      }
+    }
+    float mean = 0.f;
+#pragma unroll
+    for (int e = 0; e < PE_E; ++e) mean += acc[e];
+    mean *= (1.0f / PE_E);
+    float var = 0.f;
+#pragma unroll
+    for (int e = 0; e < PE_E; ++e) {
+      const float d = acc[e] - mean;
+      var += d * d;
+    }
+    const float rstd = rsqrtf(var * (1.0f / PE_E) + 1e-5f);
+#pragma unroll
+    for (int e = 0; e < PE_E; ++e)
+      o_s[threadIdx.x * (PE_E + 1) + e] = (acc[e] - mean) * rstd * p_s[PE_E + e] + p_s[2 * PE_E + e];
+  }
+  __syncthreads();
+  const long long n_here = min((long long)PE_THREADS, total - t0);
+  float* dst = out + t0 * PE_E;
+  for (int i = threadIdx.x; i < n_here * PE_E; i += PE_THREADS) dst[i] = o_s[(i / PE_E) * (PE_E + 1) + (i % PE_E)];
+}
+
+int launch_patch_embed(const float* x, const float* w, const float* b, const float* ln_w, const float* ln_b,
+                       float* out, int B, int Cin, int H, int W, int Ho, int Wo, int scale, cudaStream_t st) {
+  SWN_CHECK(Cin >= 1 && Cin <= 4, "patch_embed: in_chans %d unsupported (1..4)", Cin);
+  const long long total = (long long)B * Ho * Wo;
+  patch_embed_kernel<<<(unsigned)((total + PE_THREADS - 1) / PE_THREADS), PE_THREADS, 0, st>>>(x, w, b, ln_w, ln_b, out, B,
+                                                                                            Cin, H, W, Ho, Wo, scale);
+  SWN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Head tail: tokens (NHWC, CI channels) -> conv3x3(CI->CM, pad 1) -> GELU -> conv1x1(CM->Cout) ->
+// NCHW output cropped to [Hout, Wout].  One thread per pixel; the 3x3 weights sit in shared memory as
+// [tap][ci][cm] and are read as broadcast float4.
+// ---------------------------------------------------------------------------------------------
+template <int CI, int CM>
+__global__ void __launch_bounds__(128) conv_head_kernel(const float* __restrict__ tok, const float* __restrict__ w1,
+                                                        const float* __restrict__ b1, const float* __restrict__ w2,
+                                                        const float* __restrict__ b2, float* __restrict__ out, int B,
+                                                        int Hh, int Wh, int Cout, int Hout, int Wout) {
+  extern __shared__ __align__(16) float cw_s[];  // [9][CI][CM] + b1[CM] + w2[Cout][CM] + b2[Cout]
+  float* b1_s = cw_s + 9 * CI * CM;
+  float* w2_s = b1_s + CM;
+  float* b2_s = w2_s + 2 * CM;
+  for (int i = threadIdx.x; i < 9 * CI * CM; i += blockDim.x) {
+    const int tap = i / (CI * CM), ci = (i / CM) % CI, cm = i % CM;  // w1 is [CM][CI][3][3]
+    cw_s[i] = w1[(cm * CI + ci) * 9 + tap];
+  }
+  for (int i = threadIdx.x; i < CM; i += blockDim.x) b1_s[i] = b1[i];
+  for (int i = threadIdx.x; i < Cout * CM; i += blockDim.x) w2_s[i] = w2[i];
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) b2_s[i] = b2[i];
+  __syncthreads();
+  const long long total = (long long)B * Hout * Wout;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int b = (int)(t / ((long long)Hout * Wout));
+  const int rem = (int)(t - (long long)b * Hout * Wout);
+  const int y = rem / Wout, x = rem - y * Wout;
+  float acc[CM];
+#pragma unroll
+  for (int m = 0; m < CM; ++m) acc[m] = b1_s[m];
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+    if (yy < 0 || yy >= Hh || xx < 0 || xx >= Wh) continue;
+    const float4* src = reinterpret_cast<const float4*>(tok + (((long long)b * Hh + yy) * Wh + xx) * CI);
+    const float* wt = cw_s + tap * CI * CM;
+#pragma unroll 2
+    for (int c4 = 0; c4 < CI / 4; ++c4) {
+      const float4 v = __ldg(src + c4);
+      const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float4* wr = reinterpret_cast<const float4*>(wt + (c4 * 4 + u) * CM);
+#pragma unroll
+        for (int m4 = 0; m4 < CM / 4; ++m4) {
+          const float4 ww = wr[m4];
+          acc[m4 * 4 + 0] = fmaf(vv[u], ww.x, acc[m4 * 4 + 0]);
+          acc[m4 * 4 + 1] = fmaf(vv[u], ww.y, acc[m4 * 4 + 1]);
+          acc[m4 * 4 + 2] = fmaf(vv[u], ww.z, acc[m4 * 4 + 2]);
+          acc[m4 * 4 + 3] = fmaf(vv[u], ww.w, acc[m4 * 4 + 3]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < CM; ++m) {
+    const float a = acc[m];
+    acc[m] = 0.5f * a * (1.0f + erff(a * 0.70710678118654752f));
+  }
+  for (int co = 0; co < Cout; ++co) {
+    float r = b2_s[co];
+#pragma unroll
+    for (int m = 0; m < CM; ++m) r = fmaf(acc[m], w2_s[co * CM + m], r);
+    out[(((long long)b * Cout + co) * Hout + y) * Wout + x] = r;
+  }
+}
+
+// bilinear upsample (align_corners=False, integer scale) of [B,Hq,Wq] to [B,Hout,Wout] (cropped)
+__global__ void bilinear_up_kernel(const float* __restrict__ lo, float* __restrict__ out, int B, int Hq, int Wq, int up,
+                                   int Hout, int Wout) {
+  const long long total = (long long)B * Hout * Wout;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int b = (int)(t / ((long long)Hout * Wout));
+  const int rem = (int)(t - (long long)b * Hout * Wout);
+  const int y = rem / Wout, x = rem - y * Wout;
+  const float inv = 1.0f / (float)up;
+  const float sy = fmaxf((y + 0.5f) * inv - 0.5f, 0.f), sx = fmaxf((x + 0.5f) * inv - 0.5f, 0.f);
+  const int y0 = min((int)sy, Hq - 1), x0 = min((int)sx, Wq - 1);
+  const int y1 = min(y0 + 1, Hq - 1), x1 = min(x0 + 1, Wq - 1);
+  const float fy = sy - (float)y0, fx = sx - (float)x0;
+  const float* p = lo + (long long)b * Hq * Wq;
+  const float top = p[y0 * Wq + x0] * (1.f - fx) + p[y0 * Wq + x1] * fx;
+  const float bot = p[y1 * Wq + x0] * (1.f - fx) + p[y1 * Wq + x1] * fx;
+  out[t] = top * (1.f - fy) + bot * fy;
+}
+
+int launch_seg_head(const float* tok, const float* w1, const float* b1, const float* w2, const float* b2, float* lowres,
+                    float* out, int B, int Hq, int Wq, int up, int Hout, int Wout, cudaStream_t st) {
+  constexpr int CI = 48, CM = 24;
+  const size_t smem = (size_t)(9 * CI * CM + CM + 2 * CM + 2) * sizeof(float);
+  SWN_CUDA(cudaFuncSetAttribute(conv_head_kernel<CI, CM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long n_lo = (long long)B * Hq * Wq;
+  conv_head_kernel<CI, CM><<<(unsigned)((n_lo + 127) / 128), 128, smem, st>>>(tok, w1, b1, w2, b2, lowres, B, Hq, Wq, 1, Hq, Wq);
+  SWN_CUDA(cudaGetLastError());
+  const long long n_hi = (long long)B * Hout * Wout;
+  bilinear_up_kernel<<<(unsigned)((n_hi + 255) / 256), 256, 0, st>>>(lowres, out, B, Hq, Wq, up, Hout, Wout);
+  SWN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_recon_head(const float* tok, const float* w1, const float* b1, const float* w2, const float* b2, float* out,
+                      int B, int Hh, int Wh, int Cout, int Hout, int Wout, cudaStream_t st) {
+  constexpr int CI = 12, CM = 12;
+  SWN_CHECK(Cout >= 1 && Cout <= 2, "recon_head: Cout must be 1 or 2");
+  SWN_CHECK(Hout <= Hh && Wout <= Wh, "recon_head: crop larger than source");
+  const size_t smem = (size_t)(9 * CI * CM + CM + 2 * CM + 2) * sizeof(float);
+  const long long n = (long long)B * Hout * Wout;
+  conv_head_kernel<CI, CM><<<(unsigned)((n + 127) / 128), 128, smem, st>>>(tok, w1, b1, w2, b2, out, B, Hh, Wh, Cout, Hout, Wout);
+  SWN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Column-block copy: dst[r, 0:cols] = src[r, 0:cols] with independent row strides (skip -> right half
+// of the decoder concat buffer).
+// ---------------------------------------------------------------------------------------------
+__global__ void copy_cols_kernel(const float4* __restrict__ src, int lds4, float4* __restrict__ dst, int ldd4,
+                                 long long rows, int cols4) {
+  const long long total = rows * cols4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols4;
+    const int c = (int)(i - r * cols4);
+    dst[r * ldd4 + c] = __ldg(src + r * lds4 + c);
+  }
+}
+int launch_copy_cols(const float* src, int lds, float* dst, int ldd, long long rows, int cols, cudaStream_t st) {
+  SWN_CHECK(cols % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0, "copy_cols: need multiples of 4");
+  const long long total = rows * (cols / 4);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  copy_cols_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(src), lds / 4,
+                                                    reinterpret_cast<float4*>(dst), ldd / 4, rows, cols / 4);
+  SWN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ST pipeline glue
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void atomic_min_f(float* a, float v) {
+  if (v >= 0.f) atomicMin(reinterpret_cast<int*>(a), __float_as_int(v));
+  else atomicMax(reinterpret_cast<unsigned*>(a), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_f(float* a, float v) {
+  if (v >= 0.f) atomicMax(reinterpret_cast<int*>(a), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned*>(a), __float_as_uint(v));
+}
+__global__ void minmax_init_kernel(float* mm, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) mm[i] = (i & 1) ? -INFINITY : INFINITY;
+}
+// seg_map = sigmoid(seg); images2 = ensure_2ch(img) (optional); masked = images * seg_map; per-(b,c) min/max
+__global__ void __launch_bounds__(256) sigmoid_mask_kernel(const float* __restrict__ img, int Cimg,
+                                                           const float* __restrict__ seg, float* __restrict__ images2,
+                                                           float* __restrict__ seg_map, float* __restrict__ masked,
+                                                           float* __restrict__ minmax, int Cout, int HW) {
+  const int b = blockIdx.z, c = blockIdx.y;
+  float lo = INFINITY, hi = -INFINITY;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+    const float sg = 1.0f / (1.0f + __expf(-seg[(long long)b * HW + i]));
+    float v;
+    if (c < Cimg) v = img[((long long)b * Cimg + c) * HW + i];
+    else v = sqrtf(fabsf(img[((long long)b * Cimg) * HW + i]));
+    if (images2) images2[((long long)b * Cout + c) * HW + i] = v;
+    if (c == 0 && seg_map) seg_map[(long long)b * HW + i] = sg;
+    const float mv = v * sg;
+    masked[((long long)b * Cout + c) * HW + i] = mv;
+    lo = fminf(lo, mv);
+    hi = fmaxf(hi, mv);
+  }
+  if (minmax) {
+    lo = -warp_max(-lo);
+    hi = warp_max(hi);
+    __shared__ float slo[8], shi[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { slo[warp] = lo; shi[warp] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < 8; ++w) { lo = fminf(lo, slo[w]); hi = fmaxf(hi, shi[w]); }
+      atomic_min_f(minmax + ((long long)b * Cout + c) * 2, lo);
+      atomic_max_f(minmax + ((long long)b * Cout + c) * 2 + 1, hi);
+    }
+  }
+}
+int launch_sigmoid_mask(const float* img, int Cimg, const float* seg, float* images2, float* seg_map, float* masked,
+                        float* minmax, int B, int Cout, int H, int W, cudaStream_t st) {
+  SWN_CHECK(Cout == Cimg || (Cimg == 1 && Cout == 2 && images2), "sigmoid_mask: bad channel configuration");
+  if (minmax) {
+    minmax_init_kernel<<<(B * Cout * 2 + 255) / 256, 256, 0, st>>>(minmax, B * Cout * 2);
+    SWN_CUDA(cudaGetLastError());
+  }
+  const int HW = H * W;
+  int bx = (HW + 255) / 256;
+  if (bx > 64) bx = 64;
+  dim3 grid(bx, Cout, B);
+  sigmoid_mask_kernel<<<grid, 256, 0, st>>>(img, Cimg, seg, images2, seg_map, masked, minmax, Cout, HW);
+  SWN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// normalize_piecewise / denormalize_piecewise; minmax is [B*C][2]
+__global__ void normalize_kernel(const float* __restrict__ x, const float* __restrict__ minmax, float* __restrict__ out,
+                                 int HW, float thr, float eps, int inverse) {
+  const int bc = blockIdx.y;
+  const float lo = minmax[bc * 2], hi = minmax[bc * 2 + 1];
+  const float range = hi - lo + eps;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+    const float v = x[(long long)bc * HW + i];
+    float r;
+    if (!inverse) {
+      const float x01 = (v - lo) / range;
+      r = x01 > thr ? log1pf(x01) : x01;
+    } else {
+      const float x01 = v > thr ? expm1f(v) : v;
+      r = x01 * range + lo;
+    }
+    out[(long long)bc * HW + i] = r;
+  }
+}
+int launch_normalize(const float* x, const float* minmax, float* out, int BC, int H, int W, float thr, float eps,
+                     int inverse, cudaStream_t st) {
+  const int HW = H * W;
+  int bx = (HW + 255) / 256;
+  if (bx > 128) bx = 128;
+  dim3 grid(bx, BC);
+  normalize_kernel<<<grid, 256, 0, st>>>(x, minmax, out, HW, thr, eps, inverse);
+  SWN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace swn

@@ -1,0 +1,90 @@
+// Internal (C++) launch interface between api.cu and the kernel translation units.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace swn {
+
+// ---- rowgemm.cu -----------------------------------------------------------------------------
+enum AMode { A_F32_LN = 0, A_F32 = 1, A_BF16 = 2, A_MERGE_LN = 3 };
+enum EMode { E_BF16 = 0, E_F32 = 1, E_EXPAND = 2 };
+
+struct RowGemmParams {
+  // A operand / prologue
+  const void* A;
+  int a_mode;
+  int M, K, lda;
+  const float* ln_w;
+  const float* ln_b;
+  float ln_eps;
+  int gH, gW, gC, gHo, gWo;  // A_MERGE_LN: source grid [B,gH,gW,gC] -> rows over [B,gHo,gWo]
+  // B operand: packed [NT x 64] bf16 SWIZZLE_128B tiles, order (chunk, kblock)
+  const __nv_bfloat16* Wp;
+  int NT, nchunks, n_valid;
+  // epilogue
+  int e_mode;
+  const float* bias;  // padded: nchunks * NT
+  void* out;
+  int ldo;
+  const float* res;
+  int ldres;
+  const float* alpha;  // device scalar (cross-attention gamma) or null
+  int xH, xW, xHs, xWs;  // E_EXPAND: source grid [B,xH,xW], output grid cropped to [xHs,xWs]
+  const float* ln2_w;
+  const float* ln2_b;
+  // filled in by the launcher
+  int stages, tmem_cols;
+};
+int launch_rowgemm(RowGemmParams p, cudaStream_t stream);
+
+// ---- mlp.cu ---------------------------------------------------------------------------------
+struct MlpParams {
+  const float* x;    // [M, C] fp32 residual stream (input)
+  float* out;        // [M, C] fp32 (may alias x)
+  int M, C;
+  const float* ln_w;
+  const float* ln_b;
+  float ln_eps;
+  const __nv_bfloat16* Wp;  // packed fc1/fc2 tile stream (see pack_mlp_weights in packing.py)
+  const float* b1;          // [4C]
+  const float* b2;          // [C16] (zero padded)
+  int HC;                   // hidden chunk width
+  int TR;                   // fc2 output rows per weight tile
+  int stages, tmem_cols;    // filled in by the launcher
+};
+int launch_mlp(MlpParams p, cudaStream_t stream);
+
+// ---- window_attn.cu -------------------------------------------------------------------------
+struct WinAttnParams {
+  const __nv_bfloat16* qkv;  // [B*H*W, 3C] token order
+  __nv_bfloat16* out;        // [B*H*W, C]
+  const float* qkv_bias;     // [3C]: q/k/v of zero-padded tokens (pad happens after norm1)
+  const float* rpb_table;    // [81, nH]
+  int B, H, W, C, nH, shift;
+};
+int launch_window_attn(WinAttnParams p, cudaStream_t stream);
+
+// ---- cross_attn.cu --------------------------------------------------------------------------
+struct CrossAttnParams {
+  const __nv_bfloat16* q;   // [B, Lq, C]
+  const __nv_bfloat16* kv;  // [B, Lk, 2C]  (k | v)
+  __nv_bfloat16* out;       // [B, Lq, C]
+  int B, Lq, Lk, C, nH;
+};
+int launch_cross_attn(CrossAttnParams p, cudaStream_t stream);
+
+// ---- elementwise.cu -------------------------------------------------------------------------
+int launch_patch_embed(const float* x, const float* w, const float* b, const float* ln_w, const float* ln_b,
+                       float* out, int B, int Cin, int H, int W, int Ho, int Wo, int scale, cudaStream_t s);
+int launch_seg_head(const float* tok, const float* w1, const float* b1, const float* w2, const float* b2,
+                    float* lowres, float* out, int B, int Hq, int Wq, int up, int Hout, int Wout, cudaStream_t s);
+int launch_recon_head(const float* tok, const float* w1, const float* b1, const float* w2, const float* b2,
+                      float* out, int B, int Hh, int Wh, int Cout, int Hout, int Wout, cudaStream_t s);
+int launch_copy_cols(const float* src, int lds, float* dst, int ldd, long long rows, int cols, cudaStream_t s);
+int launch_sigmoid_mask(const float* img, int Cimg, const float* seg, float* images2, float* seg_map, float* masked,
+                        float* minmax, int B, int Cout, int H, int W, cudaStream_t s);
+int launch_normalize(const float* x, const float* minmax, float* out, int BC, int H, int W, float thr, float eps,
+                     int inverse, cudaStream_t s);
+
+}  // namespace swn

@@ -1,0 +1,292 @@
+// Fused Swin MLP on tcgen05 tensor cores:   out = x + fc2( GELU( fc1( LayerNorm(x) ) ) )
+// (reference: SwinTransformerBlock.norm2 + mlp + residual, SwinWNet.py:226-234,278).
+//
+// One CTA owns 128 token rows.  LayerNorm(x) is written once to shared memory as the resident bf16 A
+// operand.  The 4C hidden dimension is processed in chunks of HC columns:
+//     GEMM1  Hacc[128 x HC]  = A[128 x C] * W1_j^T        (TMEM, double buffered)
+//     epilogue-1 (4 warps)   : +b1, exact GELU, -> bf16 swizzled smem tile Hs (double buffered)
+//     GEMM2  Y[128 x C]     += Hs[128 x HC] * W2_j^T      (TMEM, resident across chunks)
+// so the 4C-wide hidden activation never leaves the SM.  GEMM1 of chunk j+1 is issued before GEMM2 of
+// chunk j, which keeps the tensor pipe busy while the epilogue warps run GELU on chunk j.  Weights are
+// streamed as pre-swizzled tiles through a TMA-engine (cp.async.bulk) mbarrier ring in exactly the
+// order the MMA warp consumes them.  Final epilogue: Y + b2 + x -> out (fp32 residual stream).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace swn {
+
+constexpr int MLP_THREADS = 192;
+constexpr int MLP_PRO_THREADS = 160;
+
+struct MlpSmem {
+  uint64_t full[8];
+  uint64_t empty[8];
+  uint64_t hacc_full[2], hacc_empty[2], hs_full[2], hs_empty[2];
+  uint64_t a_ready, y_full;
+  uint32_t tmem_base;
+};
+
+template <int KV>
+__global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(const MlpParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+
+  const int C = p.C, C16 = (C + 15) & ~15;
+  const int KB1 = (C16 + 63) >> 6, steps1 = C16 >> 4;
+  const int HC = p.HC, TR = p.TR;
+  const int nj = (4 * C) / HC;
+  const int nkk = (HC + 63) >> 6, steps2 = HC >> 4;
+  const int nT = C16 / TR;
+  const int hbase = (C16 + 31) & ~31;  // TMEM column of the first hidden accumulator
+  const int stage_bytes = max(HC, TR) * 128;
+  const int w1_bytes = HC * 128, w2_bytes = TR * 128;
+
+  uint8_t* a_smem = smem;
+  uint8_t* hs_smem = a_smem + KB1 * A_KBLOCK_BYTES;               // 2 x nkk k-blocks
+  uint8_t* ring = hs_smem + 2 * nkk * A_KBLOCK_BYTES;
+  float* b1s = reinterpret_cast<float*>(ring + p.stages * stage_bytes);  // [4C]
+  float* b2s = b1s + 4 * C;                                              // [C16]
+  MlpSmem* sh = reinterpret_cast<MlpSmem*>(b2s + C16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long m0 = (long long)blockIdx.x * TILE_M;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&sh->full[s], 1);
+      mbar_init(&sh->empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&sh->hacc_full[b], 1);
+      mbar_init(&sh->hacc_empty[b], 128);
+      mbar_init(&sh->hs_full[b], 128);
+      mbar_init(&sh->hs_empty[b], 1);
+    }
+    mbar_init(&sh->a_ready, MLP_PRO_THREADS);
+    mbar_init(&sh->y_full, 1);
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < 4 * C; i += MLP_THREADS) b1s[i] = p.b1[i];
+  for (int i = threadIdx.x; i < C16; i += MLP_THREADS) b2s[i] = p.b2[i];
+  if (warp == 0) tmem_alloc(&sh->tmem_base, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sh->tmem_base;
+
+  if (warp == 0) {
+    // ===== weight producer (consumption order: G1(0), [G1(j+1), G2(j)]..., G2(nj-1)) =====
+    if (lane == 0) {
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(p.Wp);
+      int t = 0;
+      auto push = [&](int bytes) {
+        const int s = t % p.stages;
+        mbar_wait(&sh->empty[s], ((uint32_t)(t / p.stages) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(&sh->full[s], (uint32_t)bytes);
+        bulk_g2s(ring + s * stage_bytes, src, (uint32_t)bytes, &sh->full[s]);
+        src += bytes;
+        ++t;
+      };
+      for (int kb = 0; kb < KB1; ++kb) push(w1_bytes);
+      for (int j = 0; j < nj; ++j) {
+        if (j + 1 < nj)
+          for (int kb = 0; kb < KB1; ++kb) push(w1_bytes);
+        for (int i = 0; i < nkk * nT; ++i) push(w2_bytes);
+      }
+    }
+  } else {
+    // ===== prologue: LayerNorm(x) -> resident bf16 A tile =====
+    for (int r = warp - 1; r < TILE_M; r += 5) {
+      const long long m = m0 + r;
+      const bool row_ok = m < p.M;
+      float4 v[KV];
+#pragma unroll
+      for (int i = 0; i < KV; ++i) {
+        const int k = (i * 32 + lane) * 4;
+        v[i] = (row_ok && k < C) ? *reinterpret_cast<const float4*>(p.x + m * C + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < KV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      const float mean = warp_sum(s) / (float)C;
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < KV; ++i) {
+        const int k = (i * 32 + lane) * 4;
+        if (k < C) {
+          float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+          q += (a * a + b * b) + (c * c + d * d);
+        }
+      }
+      const float rstd = rsqrtf(warp_sum(q) / (float)C + p.ln_eps);
+#pragma unroll
+      for (int i = 0; i < KV; ++i) {
+        const int k = (i * 32 + lane) * 4;
+        if (k < C16) {
+          uint2 o = make_uint2(0u, 0u);
+          if (row_ok && k < C) {
+            const float4 g = *reinterpret_cast<const float4*>(p.ln_w + k);
+            const float4 be = *reinterpret_cast<const float4*>(p.ln_b + k);
+            o = make_uint2(pack_bf16((v[i].x - mean) * rstd * g.x + be.x, (v[i].y - mean) * rstd * g.y + be.y),
+                           pack_bf16((v[i].z - mean) * rstd * g.z + be.z, (v[i].w - mean) * rstd * g.w + be.w));
+          }
+          *reinterpret_cast<uint2*>(a_smem + (k >> 6) * A_KBLOCK_BYTES + sw128_offset(r, k & 63)) = o;
+        }
+      }
+    }
+    fence_proxy_async();
+    mbar_arrive(&sh->a_ready);
+
+    if (warp == 1) {
+      // ===== MMA issuer =====
+      if (lane == 0) {
+        mbar_wait(&sh->a_ready, 0);
+        tc_fence_after();
+        const uint32_t idesc1 = umma_idesc_bf16(TILE_M, (uint32_t)HC);
+        const uint32_t idesc2 = umma_idesc_bf16(TILE_M, (uint32_t)TR);
+        const uint32_t a_addr = smem_u32(a_smem), hs_addr = smem_u32(hs_smem);
+        int t = 0;
+        auto gemm1 = [&](int j) {
+          const int buf = j & 1;
+          mbar_wait(&sh->hacc_empty[buf], (((uint32_t)j >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+          const uint32_t d = tmem_base + (uint32_t)(hbase + buf * HC);
+          for (int kb = 0; kb < KB1; ++kb, ++t) {
+            const int s = t % p.stages;
+            mbar_wait(&sh->full[s], (uint32_t)(t / p.stages) & 1u);
+            tc_fence_after();
+            const uint32_t b_addr = smem_u32(ring + s * stage_bytes);
+            const int steps = min(4, steps1 - kb * 4);
+            for (int k = 0; k < steps; ++k)
+              umma_bf16(d, umma_desc_sw128(a_addr + kb * A_KBLOCK_BYTES + k * 32), umma_desc_sw128(b_addr + k * 32),
+                        idesc1, (kb | k) != 0 ? 1u : 0u);
+            umma_commit(&sh->empty[s]);
+          }
+          umma_commit(&sh->hacc_full[buf]);
+        };
+        auto gemm2 = [&](int j) {
+          const int buf = j & 1;
+          mbar_wait(&sh->hs_full[buf], ((uint32_t)j >> 1) & 1u);
+          tc_fence_after();
+          const uint32_t h_addr = hs_addr + buf * nkk * A_KBLOCK_BYTES;
+          for (int kk = 0; kk < nkk; ++kk) {
+            const int steps = min(4, steps2 - kk * 4);
+            for (int tt = 0; tt < nT; ++tt, ++t) {
+              const int s = t % p.stages;
+              mbar_wait(&sh->full[s], (uint32_t)(t / p.stages) & 1u);
+              tc_fence_after();
+              const uint32_t b_addr = smem_u32(ring + s * stage_bytes);
+              for (int k = 0; k < steps; ++k)
+                umma_bf16(tmem_base + (uint32_t)(tt * TR), umma_desc_sw128(h_addr + kk * A_KBLOCK_BYTES + k * 32),
+                          umma_desc_sw128(b_addr + k * 32), idesc2, (j | kk | k) != 0 ? 1u : 0u);
+              umma_commit(&sh->empty[s]);
+            }
+          }
+          umma_commit(&sh->hs_empty[buf]);
+        };
+        gemm1(0);
+        for (int j = 0; j < nj; ++j) {
+          if (j + 1 < nj) gemm1(j + 1);
+          gemm2(j);
+        }
+        umma_commit(&sh->y_full);
+      }
+    } else {
+      // ===== epilogue warps 2..5: thread <-> row =====
+      const int lg = warp & 3;
+      const int r = lg * 32 + lane;
+      const long long m = m0 + r;
+      const bool row_ok = m < p.M;
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
+      float v[16];
+      for (int j = 0; j < nj; ++j) {
+        const int buf = j & 1;
+        const uint32_t ph = ((uint32_t)j >> 1) & 1u;
+        mbar_wait(&sh->hacc_full[buf], ph);
+        mbar_wait(&sh->hs_empty[buf], ph ^ 1u);
+        tc_fence_after();
+        uint8_t* hrow = hs_smem + buf * nkk * A_KBLOCK_BYTES;
+        const float* bj = b1s + j * HC;
+        for (int cb = 0; cb < steps2; ++cb) {
+          tmem_ld16(lane_addr + (uint32_t)(hbase + buf * HC + cb * 16), v);
+          tmem_ld_wait();
+          uint32_t pk[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float a = gelu_erf(v[2 * i] + bj[cb * 16 + 2 * i]);
+            float b = gelu_erf(v[2 * i + 1] + bj[cb * 16 + 2 * i + 1]);
+            pk[i] = pack_bf16(a, b);
+          }
+          const int k = cb * 16;
+          uint8_t* kb_base = hrow + (k >> 6) * A_KBLOCK_BYTES;
+          *reinterpret_cast<uint4*>(kb_base + sw128_offset(r, k & 63)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(kb_base + sw128_offset(r, (k & 63) + 8)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+        tc_fence_before();
+        fence_proxy_async();
+        mbar_arrive(&sh->hacc_empty[buf]);
+        mbar_arrive(&sh->hs_full[buf]);
+      }
+      mbar_wait(&sh->y_full, 0);
+      tc_fence_after();
+      for (int cb = 0; cb < (C16 >> 4); ++cb) {
+        tmem_ld16(lane_addr + (uint32_t)(cb * 16), v);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int j4 = 0; j4 < 16; j4 += 4) {
+            const int c = cb * 16 + j4;
+            if (c < C) {
+              const float4 xr = *reinterpret_cast<const float4*>(p.x + m * C + c);
+              float4 o;
+              o.x = v[j4 + 0] + b2s[c + 0] + xr.x;
+              o.y = v[j4 + 1] + b2s[c + 1] + xr.y;
+              o.z = v[j4 + 2] + b2s[c + 2] + xr.z;
+              o.w = v[j4 + 3] + b2s[c + 3] + xr.w;
+              *reinterpret_cast<float4*>(p.out + m * C + c) = o;
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+int launch_mlp(MlpParams p, cudaStream_t stream) {
+  const int C = p.C, C16 = (C + 15) & ~15;
+  SWN_CHECK(p.M > 0 && C >= 4 && C % 4 == 0 && C <= 384, "mlp: unsupported C=%d", C);
+  SWN_CHECK(p.HC % 16 == 0 && p.HC >= 16 && p.HC <= 256 && (4 * C) % p.HC == 0, "mlp: bad HC=%d for C=%d", p.HC, C);
+  SWN_CHECK(p.TR % 16 == 0 && p.TR >= 16 && p.TR <= 256 && C16 % p.TR == 0, "mlp: bad TR=%d for C=%d", p.TR, C);
+  const int nj = (4 * C) / p.HC;
+  const int KB1 = (C16 + 63) >> 6, nkk = (p.HC + 63) >> 6;
+  int cols = ((C16 + 31) & ~31) + (nj > 1 ? 2 : 1) * p.HC, tc = 32;
+  while (tc < cols) tc <<= 1;
+  SWN_CHECK(tc <= 512, "mlp: TMEM overflow (C=%d HC=%d)", C, p.HC);
+  p.tmem_cols = tc;
+  const int stage_bytes = (p.HC > p.TR ? p.HC : p.TR) * 128;
+  const int fixed = 1024 + (KB1 + 2 * nkk) * A_KBLOCK_BYTES + (4 * C + C16) * 4 + (int)sizeof(MlpSmem) + 64;
+  int stages = (232448 - fixed) / stage_bytes;
+  if (stages > 6) stages = 6;
+  SWN_CHECK(stages >= 2, "mlp: C=%d HC=%d TR=%d does not fit in shared memory", C, p.HC, p.TR);
+  p.stages = stages;
+  const size_t smem = (size_t)fixed + (size_t)stages * stage_bytes;
+  const long long grid = ((long long)p.M + TILE_M - 1) / TILE_M;
+  const int KV = (C + 127) / 128;
+  auto go = [&](auto kern) -> int {
+    SWN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)grid, MLP_THREADS, smem, stream>>>(p);
+    SWN_CUDA(cudaGetLastError());
+    return 0;
+  };
+  if (KV <= 1) return go(mlp_kernel<1>);
+  return go(mlp_kernel<3>);
+}
+
+}  // namespace swn

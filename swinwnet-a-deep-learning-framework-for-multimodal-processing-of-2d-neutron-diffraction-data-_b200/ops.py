@@ -1,0 +1,134 @@
+"""Thin torch<->C-ABI glue: unwraps data_ptr()/current stream and calls libswinwnet_b200.so.
+PyTorch is used for device memory and streams only; all math runs in the hand-written kernels."""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import RowGemmArgs
+
+A_F32_LN, A_F32, A_BF16, A_MERGE_LN = 0, 1, 2, 3
+E_BF16, E_F32, E_EXPAND = 0, 1, 2
+
+LAUNCH_COUNT = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
+_LAUNCHES_PER_CALL = {"rowgemm": 1, "mlp": 1, "window_attention": 1, "cross_attention": 1, "patch_embed": 1,
+                      "seg_head": 2, "recon_head": 1, "copy_cols": 1, "sigmoid_mask": 1, "sigmoid_mask_mm": 2,
+                      "normalize": 1}
+
+
+def _count(kind):
+    global LAUNCH_COUNT
+    LAUNCH_COUNT += _LAUNCHES_PER_CALL[kind]
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("swinwnet_b200: tensors must live on a CUDA device (no CPU fallback exists)")
+
+
+def mlp_config(C):
+    hc, tr = ctypes.c_int(0), ctypes.c_int(0)
+    _lib.check(_lib.load().swn_mlp_config(C, ctypes.byref(hc), ctypes.byref(tr)), "swn_mlp_config")
+    return hc.value, tr.value
+
+
+def rowgemm(*, A, a_mode, M, K, lda, Wp, NT, nchunks, n_valid, e_mode, out, ldo, bias=None, ln_w=None, ln_b=None,
+            ln_eps=1e-5, merge=None, res=None, ldres=0, alpha=None, expand=None, ln2_w=None, ln2_b=None):
+    _need_cuda(A, Wp, out)
+    a = RowGemmArgs()
+    a.A, a.a_mode, a.M, a.K, a.lda = _ptr(A), a_mode, M, K, lda
+    a.ln_w, a.ln_b, a.ln_eps = _ptr(ln_w), _ptr(ln_b), ln_eps
+    if merge is not None:
+        a.gH, a.gW, a.gC, a.gHo, a.gWo = merge
+    a.Wp, a.NT, a.nchunks, a.n_valid = _ptr(Wp), NT, nchunks, n_valid
+    a.e_mode, a.bias, a.out, a.ldo = e_mode, _ptr(bias), _ptr(out), ldo
+    a.res, a.ldres, a.alpha = _ptr(res), ldres, _ptr(alpha)
+    if expand is not None:
+        a.xH, a.xW, a.xHs, a.xWs = expand
+    a.ln2_w, a.ln2_b = _ptr(ln2_w), _ptr(ln2_b)
+    _lib.check(_lib.load().swn_rowgemm(ctypes.byref(a), _stream()), "swn_rowgemm")
+    _count("rowgemm")
+
+
+def mlp(x, out, M, C, ln_w, ln_b, Wp, b1, b2p, eps=1e-5):
+    _need_cuda(x, out, Wp)
+    _lib.check(_lib.load().swn_mlp(_ptr(x), _ptr(out), M, C, _ptr(ln_w), _ptr(ln_b), eps, _ptr(Wp), _ptr(b1), _ptr(b2p),
+                                   _stream()), "swn_mlp")
+    _count("mlp")
+
+
+def window_attention(qkv, out, qkv_bias, table, B, H, W, C, nH, shift=0):
+    _need_cuda(qkv, out)
+    _lib.check(_lib.load().swn_window_attention(_ptr(qkv), _ptr(out), _ptr(qkv_bias), _ptr(table), B, H, W, C, nH, shift,
+                                                _stream()), "swn_window_attention")
+    _count("window_attention")
+
+
+def cross_attention(q, kv, out, B, Lq, Lk, C, nH):
+    _need_cuda(q, kv, out)
+    _lib.check(_lib.load().swn_cross_attention(_ptr(q), _ptr(kv), _ptr(out), B, Lq, Lk, C, nH, _stream()),
+               "swn_cross_attention")
+    _count("cross_attention")
+
+
+def patch_embed(x, w, b, ln_w, ln_b, out, B, Cin, H, W, Ho, Wo, scale):
+    _need_cuda(x, out)
+    _lib.check(_lib.load().swn_patch_embed(_ptr(x), _ptr(w), _ptr(b), _ptr(ln_w), _ptr(ln_b), _ptr(out), B, Cin, H, W, Ho,
+                                           Wo, scale, _stream()), "swn_patch_embed")
+    _count("patch_embed")
+
+
+def seg_head(tok, w1, b1, w2, b2, lowres, out, B, Hq, Wq, up, Hout, Wout):
+    _need_cuda(tok, out)
+    _lib.check(_lib.load().swn_seg_head(_ptr(tok), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), _ptr(lowres), _ptr(out), B, Hq,
+                                        Wq, up, Hout, Wout, _stream()), "swn_seg_head")
+    _count("seg_head")
+
+
+def recon_head(tok, w1, b1, w2, b2, out, B, Hh, Wh, Cout, Hout, Wout):
+    _need_cuda(tok, out)
+    _lib.check(_lib.load().swn_recon_head(_ptr(tok), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), _ptr(out), B, Hh, Wh, Cout,
+                                          Hout, Wout, _stream()), "swn_recon_head")
+    _count("recon_head")
+
+
+def copy_cols(src, lds, dst_ptr_tensor, dst_col_offset, ldd, rows, cols):
+    """dst[:, dst_col_offset : dst_col_offset+cols] = src[:, :cols] (row strides lds / ldd, in floats)."""
+    _need_cuda(src, dst_ptr_tensor)
+    dst = ctypes.c_void_p(dst_ptr_tensor.data_ptr() + 4 * dst_col_offset)
+    _lib.check(_lib.load().swn_copy_cols(_ptr(src), lds, dst, ldd, rows, cols, _stream()), "swn_copy_cols")
+    _count("copy_cols")
+
+
+def sigmoid_mask(img, seg, *, ensure_2ch, want_minmax):
+    """returns (images, seg_map, masked, minmax|None) for the ST pipeline stages 1-3 / 7-8."""
+    _need_cuda(img, seg)
+    B, Cimg, H, W = img.shape
+    Cout = 2 if (ensure_2ch and Cimg != 2) else Cimg
+    images2 = torch.empty(B, Cout, H, W, device=img.device, dtype=torch.float32) if Cout != Cimg else None
+    seg_map = torch.empty(B, 1, H, W, device=img.device, dtype=torch.float32)
+    masked = torch.empty(B, Cout, H, W, device=img.device, dtype=torch.float32)
+    minmax = torch.empty(B * Cout, 2, device=img.device, dtype=torch.float32) if want_minmax else None
+    _lib.check(_lib.load().swn_sigmoid_mask(_ptr(img), Cimg, _ptr(seg), _ptr(images2), _ptr(seg_map), _ptr(masked),
+                                            _ptr(minmax), B, Cout, H, W, _stream()), "swn_sigmoid_mask")
+    _count("sigmoid_mask_mm" if want_minmax else "sigmoid_mask")
+    return (images2 if images2 is not None else img), seg_map, masked, minmax
+
+
+def normalize(x, minmax, inverse, threshold=0.01, eps=1e-6):
+    _need_cuda(x, minmax)
+    B, C, H, W = x.shape
+    out = torch.empty_like(x)
+    _lib.check(_lib.load().swn_normalize(_ptr(x), _ptr(minmax), _ptr(out), B * C, H, W, threshold, eps, int(inverse),
+                                         _stream()), "swn_normalize")
+    _count("normalize")
+    return out

@@ -1,0 +1,264 @@
+"""GPU parity tests, op level: every C-ABI entry point against the oracle's fp32 math on the same seeded
+inputs.  Tolerances: bf16 tensor-core operands with fp32 accumulation -> max abs error <= 2e-2 of the
+reference's max magnitude (north_star tolerance); fp32 CUDA-core kernels -> 1e-4."""
+import math
+
+import pytest
+import torch
+
+import swinwnet_b200 as S
+from swinwnet_b200 import ops, packing
+from oracle import swinwnet_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL_BF16 = 2e-2
+TOL_F32 = 1e-4
+
+
+def relerr(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    assert torch.isfinite(a).all(), "non-finite values in kernel output"
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-6)
+
+
+def bf(x):  # bf16 rounding of an operand, as the kernel sees it
+    return x.to(torch.bfloat16).float()
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("C,M", [(48, 300), (96, 128), (192, 257), (384, 130), (24, 1000), (12, 515)])
+def test_rowgemm_ln_qkv(C, M):
+    x = rnd(M, C, seed=1) * 2 + 0.3
+    W, b = rnd(3 * C, C, seed=2, scale=C ** -0.5), rnd(3 * C, seed=3, scale=0.1)
+    lw, lb = 1 + 0.1 * rnd(C, seed=4), 0.1 * rnd(C, seed=5)
+    ref = O.linear(O.layer_norm(x, lw, lb), W, b)
+    nv = packing.choose_chunk(3 * C, 256)
+    Wp, bp, NT, nch = packing.pack_rowgemm(W.to(DEV), b.to(DEV), nv)
+    out = torch.empty(M, 3 * C, device=DEV, dtype=torch.bfloat16)
+    ops.rowgemm(A=x.to(DEV), a_mode=ops.A_F32_LN, M=M, K=C, lda=C, ln_w=lw.to(DEV), ln_b=lb.to(DEV), Wp=Wp, NT=NT,
+                nchunks=nch, n_valid=nv, e_mode=ops.E_BF16, bias=bp, out=out, ldo=3 * C)
+    torch.cuda.synchronize()
+    assert relerr(out, ref) <= TOL_BF16
+
+
+@pytest.mark.parametrize("C,M", [(48, 300), (192, 129), (384, 256), (12, 77)])
+def test_rowgemm_bf16_proj_residual_alpha(C, M):
+    a = rnd(M, C, seed=1).to(torch.bfloat16)
+    W, b = rnd(C, C, seed=2, scale=C ** -0.5), rnd(C, seed=3, scale=0.1)
+    res = rnd(M, C, seed=4)
+    gamma = torch.tensor([0.37])
+    ref = res + gamma * O.linear(a.float(), W, b)
+    nv = packing.choose_chunk(C, 256)
+    Wp, bp, NT, nch = packing.pack_rowgemm(W.to(DEV), b.to(DEV), nv)
+    out = torch.empty(M, C, device=DEV)
+    ops.rowgemm(A=a.to(DEV), a_mode=ops.A_BF16, M=M, K=C, lda=C, Wp=Wp, NT=NT, nchunks=nch, n_valid=nv, e_mode=ops.E_F32,
+                bias=bp, out=out, ldo=C, res=res.to(DEV), ldres=C, alpha=gamma.to(DEV))
+    torch.cuda.synchronize()
+    assert relerr(out, ref) <= TOL_BF16
+
+
+def test_rowgemm_inplace_residual():
+    C, M = 96, 200
+    a = rnd(M, C, seed=1).to(torch.bfloat16)
+    W, b = rnd(C, C, seed=2, scale=C ** -0.5), rnd(C, seed=3, scale=0.1)
+    x = rnd(M, C, seed=4)
+    ref = x + O.linear(a.float(), W, b)
+    Wp, bp, NT, nch = packing.pack_rowgemm(W.to(DEV), b.to(DEV), C)
+    xd = x.to(DEV)
+    ops.rowgemm(A=a.to(DEV), a_mode=ops.A_BF16, M=M, K=C, lda=C, Wp=Wp, NT=NT, nchunks=nch, n_valid=C, e_mode=ops.E_F32,
+                bias=bp, out=xd, ldo=C, res=xd, ldres=C)
+    torch.cuda.synchronize()
+    assert relerr(xd, ref) <= TOL_BF16
+
+
+@pytest.mark.parametrize("C,H,W", [(48, 9, 13), (96, 8, 6), (192, 5, 5)])
+def test_rowgemm_patch_merging(C, H, W):
+    B = 2
+    x = rnd(B, H * W, C, seed=1)
+    sd = {"reduction.weight": rnd(2 * C, 4 * C, seed=2, scale=(4 * C) ** -0.5), "norm.weight": 1 + 0.1 * rnd(4 * C, seed=3),
+          "norm.bias": 0.1 * rnd(4 * C, seed=4)}
+    ref, res = O.patch_merging(sd, "", x, (H, W))
+    m = S.model.PatchMerging(C).to(DEV)
+    m.load_state_dict(sd)
+    with torch.no_grad():
+        out, res2 = m(x.to(DEV), (H, W))
+    torch.cuda.synchronize()
+    assert tuple(res2) == tuple(res)
+    assert relerr(out, ref) <= TOL_BF16
+
+
+@pytest.mark.parametrize("C,H,W,crop", [(384, 4, 6, None), (96, 5, 7, (9, 13)), (48, 6, 5, None), (24, 10, 12, None)])
+def test_rowgemm_patch_expanding(C, H, W, crop):
+    B = 2
+    x = rnd(B, H * W, C, seed=1)
+    sd = {"expand.weight": rnd(2 * C, C, seed=2, scale=C ** -0.5), "norm.weight": 1 + 0.1 * rnd(C // 2, seed=3),
+          "norm.bias": 0.1 * rnd(C // 2, seed=4)}
+    ref, res = O.patch_expanding(sd, "", x, (H, W))
+    if crop is not None:
+        ref = O.crop_tokens(ref, res, crop)
+    m = S.model.PatchExpanding(C).to(DEV)
+    m.load_state_dict(sd)
+    with torch.no_grad():
+        out, _ = m.run(x.to(DEV), (H, W), crop)
+    torch.cuda.synchronize()
+    assert relerr(out, ref) <= TOL_BF16
+
+
+@pytest.mark.parametrize("C,M", [(48, 300), (96, 128), (192, 200), (384, 129), (24, 700), (12, 1025)])
+def test_fused_mlp(C, M):
+    x = rnd(M, C, seed=1)
+    W1, b1 = rnd(4 * C, C, seed=2, scale=C ** -0.5), rnd(4 * C, seed=3, scale=0.2)
+    W2, b2 = rnd(C, 4 * C, seed=4, scale=(4 * C) ** -0.5), rnd(C, seed=5, scale=0.1)
+    lw, lb = 1 + 0.1 * rnd(C, seed=6), 0.1 * rnd(C, seed=7)
+    ref = x + O.linear(O.gelu_erf(O.linear(O.layer_norm(x, lw, lb), W1, b1)), W2, b2)
+    HC, TR = ops.mlp_config(C)
+    Wp, b2p = packing.pack_mlp(W1.to(DEV), W2.to(DEV), b2.to(DEV), HC, TR)
+    xd = x.to(DEV)
+    out = torch.empty_like(xd)
+    ops.mlp(xd, out, M, C, lw.to(DEV), lb.to(DEV), Wp, b1.to(DEV), b2p)
+    torch.cuda.synchronize()
+    assert relerr(out, ref) <= TOL_BF16
+    ops.mlp(xd, xd, M, C, lw.to(DEV), lb.to(DEV), Wp, b1.to(DEV), b2p)  # in place
+    torch.cuda.synchronize()
+    assert relerr(xd, ref) <= TOL_BF16
+
+
+def _win_attn_ref(qkv, bias, table, B, H, W, C, nH, shift):
+    """oracle window attention fed with a given token-ordered qkv tensor (pads take the bias)."""
+    ws, hd = 5, C // nH
+    g = qkv.view(B, H, W, 3 * C)
+    if shift:
+        g = torch.roll(g, (-shift, -shift), (1, 2))
+    Hp, Wp = -(-H // ws) * ws, -(-W // ws) * ws
+    gp = bias.view(1, 1, 1, -1).expand(B, Hp, Wp, 3 * C).clone()
+    gp[:, :H, :W] = g
+    nWy, nWx = Hp // ws, Wp // ws
+    win = gp.view(B, nWy, ws, nWx, ws, 3, nH, hd).permute(0, 1, 3, 5, 6, 2, 4, 7).reshape(B * nWy * nWx, 3, nH, 25, hd)
+    q, k, v = win[:, 0] * hd ** -0.5, win[:, 1], win[:, 2]
+    att = q @ k.transpose(-1, -2) + table[O.rel_pos_index(ws).reshape(-1)].view(25, 25, nH).permute(2, 0, 1)[None]
+    if shift:
+        rid = O.shift_region_ids(Hp, Wp, ws, shift).view(nWy, ws, nWx, ws).permute(0, 2, 1, 3).reshape(nWy * nWx, 25)
+        m = torch.where(rid[:, :, None] == rid[:, None, :], 0.0, -100.0)
+        att = (att.view(B, nWy * nWx, nH, 25, 25) + m[None, :, None]).view(-1, nH, 25, 25)
+    o = (torch.softmax(att, -1) @ v).permute(0, 2, 1, 3).reshape(B, nWy, nWx, ws, ws, C).permute(0, 1, 3, 2, 4, 5)
+    o = o.reshape(B, Hp, Wp, C)
+    if shift:
+        o = torch.roll(o, (shift, shift), (1, 2))
+    return o[:, :H, :W].reshape(B * H * W, C)
+
+
+@pytest.mark.parametrize("C,nH,H,W,shift", [(48, 3, 10, 15, 0), (96, 6, 7, 11, 0), (384, 24, 4, 6, 0), (384, 12, 8, 5, 0),
+                                            (192, 6, 5, 10, 0), (24, 3, 10, 10, 0), (12, 3, 12, 9, 0), (48, 3, 10, 15, 2),
+                                            (96, 3, 5, 5, 3)])
+def test_window_attention(C, nH, H, W, shift):
+    B = 2
+    qkv = rnd(B * H * W, 3 * C, seed=1).to(torch.bfloat16)
+    bias, table = rnd(3 * C, seed=2, scale=0.3), rnd(81, nH, seed=3, scale=0.5)
+    ref = _win_attn_ref(qkv.float(), bf(bias), table, B, H, W, C, nH, shift)
+    out = torch.empty(B * H * W, C, device=DEV, dtype=torch.bfloat16)
+    ops.window_attention(qkv.to(DEV), out, bias.to(DEV), table.to(DEV), B, H, W, C, nH, shift)
+    torch.cuda.synchronize()
+    assert relerr(out, ref) <= 1e-2
+
+
+@pytest.mark.parametrize("C,Lq,Lk", [(192, 100, 75), (384, 70, 130), (192, 64, 64), (384, 12, 40), (192, 480, 1920)])
+def test_cross_attention_core(C, Lq, Lk):
+    B, nH = 2, 3
+    hd = C // nH
+    q = rnd(B, Lq, C, seed=1).to(torch.bfloat16)
+    kv = rnd(B, Lk, 2 * C, seed=2).to(torch.bfloat16)
+    Q = q.float().view(B, Lq, nH, hd).permute(0, 2, 1, 3)
+    K = kv.float()[..., :C].reshape(B, Lk, nH, hd).permute(0, 2, 1, 3)
+    V = kv.float()[..., C:].reshape(B, Lk, nH, hd).permute(0, 2, 1, 3)
+    ref = (torch.softmax(Q @ K.transpose(-1, -2) * hd ** -0.5, -1) @ V).permute(0, 2, 1, 3).reshape(B, Lq, C)
+    out = torch.empty(B, Lq, C, device=DEV, dtype=torch.bfloat16)
+    ops.cross_attention(q.to(DEV), kv.to(DEV), out, B, Lq, Lk, C, nH)
+    torch.cuda.synchronize()
+    assert relerr(out, ref) <= 1.5e-2
+
+
+@pytest.mark.parametrize("Cin,H,W,s", [(2, 40, 60, 1), (1, 35, 51, 1), (2, 80, 120, 2), (1, 250, 480, 1)])
+def test_patch_embed(Cin, H, W, s):
+    B = 2
+    x = rnd(B, Cin, H, W, seed=1) * 3
+    sd = {"proj.weight": rnd(48, Cin, 2, 2, seed=2, scale=0.5), "proj.bias": rnd(48, seed=3, scale=0.1),
+          "norm.weight": 1 + 0.1 * rnd(48, seed=4), "norm.bias": 0.1 * rnd(48, seed=5)}
+    ref, pres = O.patch_embed(sd, "", x, s)
+    m = S.model.ScaleAwarePatchEmbed(2, Cin, 48).to(DEV)
+    m.load_state_dict(sd)
+    with torch.no_grad():
+        out, pres2 = m(x.to(DEV), scale_factor=s)
+    torch.cuda.synchronize()
+    assert tuple(pres) == tuple(pres2)
+    assert relerr(out, ref) <= TOL_F32
+
+
+@pytest.mark.parametrize("scale", [1, 2])
+def test_segmentation_head(scale):
+    B, Hq, Wq = 2, 9, 14
+    x = rnd(B, Hq * Wq, 48, seed=1)
+    sd = {"seg_head.0.weight": rnd(24, 48, 3, 3, seed=2, scale=0.05), "seg_head.0.bias": rnd(24, seed=3, scale=0.1),
+          "seg_head.2.weight": rnd(1, 24, 1, 1, seed=4, scale=0.2), "seg_head.2.bias": rnd(1, seed=5, scale=0.1)}
+    res = (Hq * 2 * scale, Wq * 2 * scale)
+    ref = O.segmentation_head(sd, "", x, res, scale)
+    m = S.model.SegmentationHead().to(DEV)
+    m.load_state_dict(sd)
+    with torch.no_grad():
+        out = m(x.to(DEV), res, scale_factor=scale)
+    torch.cuda.synchronize()
+    assert relerr(out, ref) <= TOL_F32
+
+
+def test_recon_head_and_glue():
+    B, H, W = 2, 12, 20
+    x = rnd(B, H * W, 12, seed=1)
+    w1, b1 = rnd(12, 12, 3, 3, seed=2, scale=0.1), rnd(12, seed=3, scale=0.1)
+    w2, b2 = rnd(2, 12, 1, 1, seed=4, scale=0.3), rnd(2, seed=5, scale=0.1)
+    h = O.gelu_erf(O.conv3x3_nhwc(x.view(B, H, W, 12), w1, b1))
+    ref = (h @ w2.view(2, 12).t() + b2).permute(0, 3, 1, 2)[:, :, :10, :18]
+    out = torch.empty(B, 2, 10, 18, device=DEV)
+    ops.recon_head(x.to(DEV), w1.to(DEV), b1.to(DEV), w2.to(DEV), b2.to(DEV), out, B, H, W, 2, 10, 18)
+    torch.cuda.synchronize()
+    assert relerr(out, ref) <= TOL_F32
+    # glue: ensure_2ch + sigmoid mask + minmax + normalize / denormalize round trip
+    img = rnd(B, 1, H, W, seed=6).abs() * 100 + 5
+    seg = rnd(B, 1, H, W, seed=7)
+    images, seg_map, masked, mm = ops.sigmoid_mask(img.to(DEV), seg.to(DEV), ensure_2ch=True, want_minmax=True)
+    ref_img = O.ensure_2ch(img)
+    ref_masked = ref_img * torch.sigmoid(seg)
+    ref_norm, params = O.normalize_piecewise(ref_masked)
+    assert relerr(images, ref_img) <= 1e-6 and relerr(seg_map, torch.sigmoid(seg)) <= 1e-5
+    assert relerr(masked, ref_masked) <= 1e-5
+    assert relerr(mm.view(B, 2, 2)[..., 0], params[0].view(B, 2)) <= 1e-5
+    assert relerr(mm.view(B, 2, 2)[..., 1], params[1].view(B, 2)) <= 1e-5
+    norm = ops.normalize(masked, mm, inverse=False)
+    assert relerr(norm, ref_norm) <= 1e-5
+    den = ops.normalize(norm, mm, inverse=True)
+    assert relerr(den, O.denormalize_piecewise(ref_norm, params)) <= 1e-5
+
+
+def test_copy_cols():
+    src = rnd(37, 48, seed=1).to(DEV)
+    dst = torch.zeros(37, 96, device=DEV)
+    ops.copy_cols(src, 48, dst, 48, 96, 37, 48)
+    torch.cuda.synchronize()
+    assert torch.equal(dst[:, 48:], src) and dst[:, :48].abs().max().item() == 0
+
+
+def test_errors_are_loud():
+    with pytest.raises(RuntimeError):
+        ops.rowgemm(A=torch.zeros(4, 6, device=DEV), a_mode=ops.A_F32, M=4, K=6, lda=6, Wp=torch.zeros(8, device=DEV),
+                    NT=16, nchunks=1, n_valid=4, e_mode=ops.E_F32, out=torch.zeros(4, 4, device=DEV), ldo=4)
+    with pytest.raises(RuntimeError):
+        ops.window_attention(torch.zeros(25, 30, device=DEV, dtype=torch.bfloat16),
+                             torch.zeros(25, 10, device=DEV, dtype=torch.bfloat16), torch.zeros(30, device=DEV),
+                             torch.zeros(81, 1, device=DEV), 1, 5, 5, 10, 1, 0)   # head_dim 10 unsupported
+    with pytest.raises(RuntimeError):
+        S.SwinWNet(depths=[2, 2, 2, 2]).segment_1(torch.zeros(1, 1, 20, 20))    # CPU tensor: no fallback

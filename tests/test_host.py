@@ -1,0 +1,115 @@
+"""CPU-only tests: host logic (weight packing, module/state_dict contract, launch planning) and the C-ABI
+library surface.  No kernel is launched here."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import swinwnet_b200 as S
+from swinwnet_b200 import _lib, packing
+from oracle import swinwnet_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+D2 = [2, 2, 2, 2]
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "swinwnet_b200.h")).read()
+    declared = set(re.findall(r"\b(swn_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"swn_rowgemm_args"}
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.swn_abi_version() == 1
+    assert ctypes.sizeof(_lib.RowGemmArgs) == lib.swn_sizeof_rowgemm_args()
+
+
+def test_mlp_config_host_call_and_errors():
+    lib = _lib.load()
+    for C, exp in ((12, (48, 16)), (24, (96, 32)), (48, (64, 48)), (96, (128, 96)), (192, (128, 192)), (384, (64, 192))):
+        hc, tr = ctypes.c_int(), ctypes.c_int()
+        assert lib.swn_mlp_config(C, ctypes.byref(hc), ctypes.byref(tr)) == 0
+        assert (hc.value, tr.value) == exp, (C, hc.value, tr.value)
+    hc, tr = ctypes.c_int(), ctypes.c_int()
+    assert lib.swn_mlp_config(13, ctypes.byref(hc), ctypes.byref(tr)) != 0
+    assert b"unsupported" in lib.swn_last_error()
+
+
+@pytest.mark.parametrize("name,ctor", [
+    ("wnet_em", lambda: S.SwinWNet(error_matrix=True, depths=D2)),
+    ("wnet", lambda: S.SwinWNet(depths=D2)),
+    ("unet", lambda: S.SwinUNet(depths=D2)),
+    ("unetsr", lambda: S.SwinUNetSR(depths=D2)),
+    ("wnet_em_default_depths", lambda: S.SwinWNet(error_matrix=True)),
+])
+def test_state_dict_contract_matches_reference(manifest, name, ctor):
+    """same keys and shapes as the reference modules (606 tensors for the multimodal model)."""
+    m = ctor()
+    sd = {k: list(v.shape) for k, v in m.state_dict().items()}
+    assert sd == manifest[name]
+    m.load_state_dict(O.make_state_dict(manifest[name], seed=0), strict=True)
+    if name == "wnet_em":
+        assert len(sd) == 606 and sum(p.numel() for p in m.parameters()) == 29159743
+        for attr in ("patch_embed", "segmentator_encoder", "segmentator_bottleneck", "segmentator_decoder",
+                     "segmentator_head", "ca_seg_to_sr", "ca_sr_to_seg", "upscaler_encoder", "upscaler_bottleneck",
+                     "upscaler_decoder", "upscaler_head"):
+            assert len(list(getattr(m, attr).parameters())) > 0
+        assert torch.equal(m.segmentator_encoder.layers[0].blocks[0].attn.relative_position_index, O.rel_pos_index(5))
+
+
+def _tile_element(flat, tile_rows, tile_idx, r, k):
+    """read element (r,k) of tile `tile_idx` the way the UMMA SWIZZLE_128B descriptor addresses it"""
+    base = tile_idx * tile_rows * 64
+    off = (r * 128 + ((((k >> 3) ^ r) & 7) << 4) + (k & 7) * 2) // 2
+    return flat[base + off]
+
+
+def test_pack_rowgemm_layout():
+    N, K, nv = 288, 96, 144
+    W = torch.randn(N, K)
+    b = torch.randn(N)
+    Wp, bp, NT, nch = packing.pack_rowgemm(W, b, nv)
+    assert (NT, nch) == (144, 2) and Wp.dtype == torch.bfloat16 and Wp.numel() == nch * 2 * NT * 64
+    Wb = W.to(torch.bfloat16)
+    for (n, kb, r, k) in [(0, 0, 0, 0), (1, 1, 143, 31), (1, 0, 77, 63), (0, 1, 9, 17)]:
+        assert _tile_element(Wp, NT, n * 2 + kb, r, k) == Wb[n * nv + r, kb * 64 + k]
+    assert _tile_element(Wp, NT, 1, 5, 40) == 0          # k = 64+40 >= K: zero padding
+    assert torch.equal(bp.view(nch, NT)[:, :nv].reshape(-1), b)
+    # padded rows (n_valid < NT)
+    Wp, bp, NT, nch = packing.pack_rowgemm(torch.randn(72, 24), None, 72)
+    assert (NT, nch) == (80, 1) and bp is None and _tile_element(Wp, NT, 0, 75, 3) == 0
+
+
+def test_pack_mlp_stream_order():
+    C, HC, TR = 96, 128, 96
+    W1, W2, b2 = torch.randn(4 * C, C), torch.randn(C, 4 * C), torch.randn(C)
+    Wp, b2p = packing.pack_mlp(W1, W2, b2, HC, TR)
+    KB1, nj, nkk, nT = 2, 3, 2, 1
+    g1, g2 = KB1 * HC * 64, nkk * nT * TR * 64
+    assert Wp.numel() == nj * (g1 + g2) and torch.equal(b2p, b2)
+    # stream: G1(0) G1(1) G2(0) G1(2) G2(1) G2(2)
+    off = {"g1_0": 0, "g1_1": g1, "g2_0": 2 * g1, "g1_2": 2 * g1 + g2, "g2_1": 3 * g1 + g2, "g2_2": 3 * g1 + 2 * g2}
+    W1b, W2b = W1.to(torch.bfloat16), W2.to(torch.bfloat16)
+    assert _tile_element(Wp[off["g1_2"]:], HC, 1, 100, 20) == W1b[2 * HC + 100, 64 + 20]
+    assert _tile_element(Wp[off["g2_1"]:], TR, 1, 50, 7) == W2b[50, 1 * HC + 64 + 7]
+    assert _tile_element(Wp[off["g2_0"]:], TR, 0, 95, 63) == W2b[95, 63]
+
+
+def test_choose_chunk():
+    assert [packing.choose_chunk(n) for n in (144, 288, 576, 1152, 72, 36, 48, 384, 768)] == \
+        [144, 144, 192, 192, 72, 36, 48, 192, 256]
+    assert packing.choose_chunk(384, 128) == 128
+
+
+def test_forward_refuses_cpu_and_autograd():
+    m = S.SwinUNet(depths=D2)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        with torch.no_grad():
+            m(torch.zeros(1, 1, 20, 20))
+    pkg = os.path.dirname(S.__file__)
+    for f in os.listdir(pkg):
+        if f.endswith(".py"):
+            assert "oracle" not in open(os.path.join(pkg, f)).read(), f"product file {f} must not reference the oracle"
