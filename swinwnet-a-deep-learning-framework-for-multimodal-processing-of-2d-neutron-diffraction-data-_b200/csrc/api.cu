@@ -16,7 +16,9 @@ void set_error(const char* fmt, ...) {
 }
 static void mlp_config(int C, int* HC, int* TR) {
   const int C16 = (C + 15) & ~15, Hd = 4 * C, hbase = (C16 + 31) & ~31;
-  if (Hd % 128 == 0 && hbase + 256 <= 512) *HC = 128;
+  // C <= 96: HC = 64 keeps smem/TMEM small enough for two co-resident CTAs per SM (these widths are bound by the
+  // CUDA-core epilogue, not the tensor pipe); wider layers use HC = 128 (full-rate N) when TMEM allows.
+  if (C > 96 && Hd % 128 == 0 && hbase + 256 <= 512) *HC = 128;
   else if (Hd % 64 == 0) *HC = 64;
   else *HC = Hd;
   *TR = C16 <= 256 ? C16 : C16 / 2;

@@ -52,22 +52,31 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
-// exact-erf GELU (nn.GELU default).  erf via Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7) on the
-// SFU (ex2 + rcp) — ~14 instructions, far below the bf16 rounding that follows it.
-__device__ __forceinline__ float erf_fast(float x) {
-  float z = fabsf(x);
-  float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+// exact-erf GELU (nn.GELU default).  erf via Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7; 6.7e-7 on GELU in
+// fp32) with the SFU approximations ex2.approx / rcp.approx: 12 FMA/ALU-pipe + 2 MUFU instructions per element,
+// three orders of magnitude below the bf16 rounding that follows it.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float ax = fabsf(x);
+  const float t = rcp_approx(fmaf(0.3275911f * 0.70710678118654752f, ax, 1.0f));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
   p = fmaf(p, t, 0.254829592f);
   p *= t;
-  float e = exp2f(-1.4426950408889634f * z * z);
-  float r = fmaf(-p, e, 1.0f);
-  return copysignf(r, x);
-}
-__device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752f));
+  const float e = ex2_approx(-0.5f * 1.4426950408889634f * x * x);  // exp(-(x/sqrt2)^2)
+  const float r = fmaf(-p, e, 1.0f);                                 // erf(|x|/sqrt2)
+  const float hx = 0.5f * x;
+  return fmaf(fabsf(hx), r, hx);                                     // 0.5x(1 + sign(x) r)
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -181,6 +190,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
+// same, 32 consecutive columns
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  __syncwarp();
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------
@@ -195,5 +217,89 @@ __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t k) {
 constexpr int TILE_M = 128;                 // rows per CTA tile = UMMA M
 constexpr int KBLK = 64;                    // bf16 elements per swizzle row
 constexpr int A_KBLOCK_BYTES = TILE_M * 128;  // one [128 x 64] bf16 k-block
+
+// ---------------------------------------------------------------------------------------------
+// Resident A-tile builder shared by the row-tile kernels.  Rows of the 128-row tile are distributed over
+// `nwarps` warps; LPR lanes cooperate on one row (so a warp covers 32/LPR rows at once — small channel
+// counts keep their lanes busy) and UNR row groups are in flight per warp (all global loads are issued
+// before the first reduction, which hides DRAM latency).  `load(row, k)` returns 4 consecutive fp32
+// source values (zeros outside the matrix); optional LayerNorm over K; bf16 result is written in the
+// K-major SWIZZLE_128B image; columns K..K16 and invalid rows are zero filled.
+// ---------------------------------------------------------------------------------------------
+template <int LPR, int KV, int UNR, bool LN, class Load>
+__device__ __forceinline__ void build_a_tile(uint8_t* a_smem, int K, int K16, const float* __restrict__ ln_w,
+                                             const float* __restrict__ ln_b, float eps, int warp, int nwarps, int lane,
+                                             Load load) {
+  constexpr int RPW = 32 / LPR;          // rows per warp pass
+  const int sub = lane / LPR, sl = lane % LPR;
+  const float inv_k = 1.0f / (float)K;
+  for (int g0 = warp * UNR; g0 < TILE_M / RPW; g0 += nwarps * UNR) {
+    float4 v[UNR][KV];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int r = (g0 + u) * RPW + sub;
+#pragma unroll
+      for (int i = 0; i < KV; ++i) {
+        const int k = (i * LPR + sl) * 4;
+        v[u][i] = (r < TILE_M && k < K) ? load(r, k) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    if (LN) {
+      float mean[UNR], rstd[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < KV; ++i) s += (v[u][i].x + v[u][i].y) + (v[u][i].z + v[u][i].w);
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        mean[u] = s * inv_k;
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < KV; ++i) {
+          const int k = (i * LPR + sl) * 4;
+          if (k < K) {
+            const float a = v[u][i].x - mean[u], b = v[u][i].y - mean[u], c = v[u][i].z - mean[u], d = v[u][i].w - mean[u];
+            q += (a * a + b * b) + (c * c + d * d);
+          }
+        }
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        rstd[u] = rsqrtf(q * inv_k + eps);
+      }
+#pragma unroll
+      for (int i = 0; i < KV; ++i) {
+        const int k = (i * LPR + sl) * 4;
+        if (k < K) {
+          const float4 gw = *reinterpret_cast<const float4*>(ln_w + k);
+          const float4 gb = *reinterpret_cast<const float4*>(ln_b + k);
+#pragma unroll
+          for (int u = 0; u < UNR; ++u) {
+            v[u][i].x = (v[u][i].x - mean[u]) * rstd[u] * gw.x + gb.x;
+            v[u][i].y = (v[u][i].y - mean[u]) * rstd[u] * gw.y + gb.y;
+            v[u][i].z = (v[u][i].z - mean[u]) * rstd[u] * gw.z + gb.z;
+            v[u][i].w = (v[u][i].w - mean[u]) * rstd[u] * gw.w + gb.w;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int r = (g0 + u) * RPW + sub;
+#pragma unroll
+      for (int i = 0; i < KV; ++i) {
+        const int k = (i * LPR + sl) * 4;
+        if (r < TILE_M && k < K16) {
+          const uint2 o = (k < K) ? make_uint2(pack_bf16(v[u][i].x, v[u][i].y), pack_bf16(v[u][i].z, v[u][i].w))
+                                  : make_uint2(0u, 0u);
+          *reinterpret_cast<uint2*>(a_smem + (k >> 6) * A_KBLOCK_BYTES + sw128_offset(r, k & 63)) = o;
+        }
+      }
+    }
+  }
+}
 
 }  // namespace swn

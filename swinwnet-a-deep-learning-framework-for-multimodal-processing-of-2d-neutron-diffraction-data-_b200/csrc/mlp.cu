@@ -1,10 +1,10 @@
 // Fused Swin MLP on tcgen05 tensor cores:   out = x + fc2( GELU( fc1( LayerNorm(x) ) ) )
 // (reference: SwinTransformerBlock.norm2 + mlp + residual, SwinWNet.py:226-234,278).
 //
-// One CTA owns 128 token rows.  LayerNorm(x) is written once to shared memory as the resident bf16 A
-// operand.  The 4C hidden dimension is processed in chunks of HC columns:
+// One CTA (10 warps) owns 128 token rows.  LayerNorm(x) is written once to shared memory as the resident
+// bf16 A operand (all warps, see build_a_tile).  The 4C hidden dimension is processed in chunks of HC columns:
 //     GEMM1  Hacc[128 x HC]  = A[128 x C] * W1_j^T        (TMEM, double buffered)
-//     epilogue-1 (4 warps)   : +b1, exact GELU, -> bf16 swizzled smem tile Hs (double buffered)
+//     epilogue-1 (8 warps)   : +b1, exact GELU, -> bf16 swizzled smem tile Hs (double buffered)
 //     GEMM2  Y[128 x C]     += Hs[128 x HC] * W2_j^T      (TMEM, resident across chunks)
 // so the 4C-wide hidden activation never leaves the SM.  GEMM1 of chunk j+1 is issued before GEMM2 of
 // chunk j, which keeps the tensor pipe busy while the epilogue warps run GELU on chunk j.  Weights are
@@ -15,8 +15,9 @@
 
 namespace swn {
 
-constexpr int MLP_THREADS = 192;
-constexpr int MLP_PRO_THREADS = 160;
+constexpr int MLP_WARPS = 10;
+constexpr int MLP_THREADS = MLP_WARPS * 32;
+constexpr int MLP_EPI_THREADS = 256;
 
 struct MlpSmem {
   uint64_t full[8];
@@ -26,7 +27,7 @@ struct MlpSmem {
   uint32_t tmem_base;
 };
 
-template <int KV>
+template <int LPR, int KV>
 __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(const MlpParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -59,11 +60,11 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(const MlpParams p) 
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&sh->hacc_full[b], 1);
-      mbar_init(&sh->hacc_empty[b], 128);
-      mbar_init(&sh->hs_full[b], 128);
+      mbar_init(&sh->hacc_empty[b], MLP_EPI_THREADS);
+      mbar_init(&sh->hs_full[b], MLP_EPI_THREADS);
       mbar_init(&sh->hs_empty[b], 1);
     }
-    mbar_init(&sh->a_ready, MLP_PRO_THREADS);
+    mbar_init(&sh->a_ready, MLP_THREADS);
     mbar_init(&sh->y_full, 1);
     fence_barrier_init();
   }
@@ -75,177 +76,179 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(const MlpParams p) 
   tc_fence_after();
   const uint32_t tmem_base = sh->tmem_base;
 
-  if (warp == 0) {
-    // ===== weight producer (consumption order: G1(0), [G1(j+1), G2(j)]..., G2(nj-1)) =====
-    if (lane == 0) {
-      const uint8_t* src = reinterpret_cast<const uint8_t*>(p.Wp);
-      int t = 0;
-      auto push = [&](int bytes) {
-        const int s = t % p.stages;
-        mbar_wait(&sh->empty[s], ((uint32_t)(t / p.stages) & 1u) ^ 1u);
-        mbar_arrive_expect_tx(&sh->full[s], (uint32_t)bytes);
-        bulk_g2s(ring + s * stage_bytes, src, (uint32_t)bytes, &sh->full[s]);
-        src += bytes;
-        ++t;
-      };
-      for (int kb = 0; kb < KB1; ++kb) push(w1_bytes);
-      for (int j = 0; j < nj; ++j) {
-        if (j + 1 < nj)
-          for (int kb = 0; kb < KB1; ++kb) push(w1_bytes);
-        for (int i = 0; i < nkk * nT; ++i) push(w2_bytes);
+  // ---- weight stream bookkeeping (consumption order: G1(0), [G1(j+1), G2(j)]..., G2(nj-1)) ----
+  // tile t -> byte size: tiles [0,KB1) are W1; then per j: (j+1<nj ? KB1 W1 tiles : none) + nkk*nT W2 tiles
+  const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.Wp);
+  int pt = 0;            // producer tile counter (thread 0 only)
+  int pj = -1, pi = 0;   // producer position: pj = -1 -> initial G1(0); else inside iteration pj, item pi
+  auto next_bytes = [&]() -> int {   // size of the next tile in stream order, 0 when the stream is exhausted
+    while (true) {
+      if (pj < 0) {
+        if (pi < KB1) { ++pi; return w1_bytes; }
+        pj = 0; pi = 0;
+      } else if (pj >= nj) {
+        return 0;
+      } else {
+        const int n1 = (pj + 1 < nj) ? KB1 : 0;
+        if (pi < n1) { ++pi; return w1_bytes; }
+        if (pi < n1 + nkk * nT) { ++pi; return w2_bytes; }
+        ++pj; pi = 0;
       }
     }
-  } else {
-    // ===== prologue: LayerNorm(x) -> resident bf16 A tile =====
-    for (int r = warp - 1; r < TILE_M; r += 5) {
-      const long long m = m0 + r;
-      const bool row_ok = m < p.M;
-      float4 v[KV];
-#pragma unroll
-      for (int i = 0; i < KV; ++i) {
-        const int k = (i * 32 + lane) * 4;
-        v[i] = (row_ok && k < C) ? *reinterpret_cast<const float4*>(p.x + m * C + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      float s = 0.f;
-#pragma unroll
-      for (int i = 0; i < KV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-      const float mean = warp_sum(s) / (float)C;
-      float q = 0.f;
-#pragma unroll
-      for (int i = 0; i < KV; ++i) {
-        const int k = (i * 32 + lane) * 4;
-        if (k < C) {
-          float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-          q += (a * a + b * b) + (c * c + d * d);
-        }
-      }
-      const float rstd = rsqrtf(warp_sum(q) / (float)C + p.ln_eps);
-#pragma unroll
-      for (int i = 0; i < KV; ++i) {
-        const int k = (i * 32 + lane) * 4;
-        if (k < C16) {
-          uint2 o = make_uint2(0u, 0u);
-          if (row_ok && k < C) {
-            const float4 g = *reinterpret_cast<const float4*>(p.ln_w + k);
-            const float4 be = *reinterpret_cast<const float4*>(p.ln_b + k);
-            o = make_uint2(pack_bf16((v[i].x - mean) * rstd * g.x + be.x, (v[i].y - mean) * rstd * g.y + be.y),
-                           pack_bf16((v[i].z - mean) * rstd * g.z + be.z, (v[i].w - mean) * rstd * g.w + be.w));
-          }
-          *reinterpret_cast<uint2*>(a_smem + (k >> 6) * A_KBLOCK_BYTES + sw128_offset(r, k & 63)) = o;
-        }
-      }
+  };
+  if (threadIdx.x == 0) {   // first ring fill before the prologue (no empty-wait needed)
+    for (; pt < p.stages; ++pt) {
+      const int bytes = next_bytes();
+      if (bytes == 0) break;
+      mbar_arrive_expect_tx(&sh->full[pt], (uint32_t)bytes);
+      bulk_g2s(ring + pt * stage_bytes, wsrc, (uint32_t)bytes, &sh->full[pt]);
+      wsrc += bytes;
     }
-    fence_proxy_async();
-    mbar_arrive(&sh->a_ready);
+  }
 
-    if (warp == 1) {
-      // ===== MMA issuer =====
-      if (lane == 0) {
-        mbar_wait(&sh->a_ready, 0);
+  // ===== prologue: LayerNorm(x) -> resident bf16 A tile (all warps) =====
+  {
+    constexpr int UNR = KV == 1 ? 4 : 2;
+    const float* x = p.x;
+    const int M = p.M;
+    build_a_tile<LPR, KV, UNR, true>(a_smem, C, C16, p.ln_w, p.ln_b, p.ln_eps, warp, MLP_WARPS, lane, [&](int r, int k) {
+      const long long m = m0 + r;
+      if (m >= M) return make_float4(0.f, 0.f, 0.f, 0.f);
+      return *reinterpret_cast<const float4*>(x + m * C + k);
+    });
+  }
+  fence_proxy_async();
+  mbar_arrive(&sh->a_ready);
+
+  if (warp == 0) {
+    // ===== weight producer: rest of the stream =====
+    if (lane == 0) {
+      while (true) {
+        const int bytes = next_bytes();
+        if (bytes == 0) break;
+        const int s = pt % p.stages;
+        mbar_wait(&sh->empty[s], ((uint32_t)(pt / p.stages) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(&sh->full[s], (uint32_t)bytes);
+        bulk_g2s(ring + s * stage_bytes, wsrc, (uint32_t)bytes, &sh->full[s]);
+        wsrc += bytes;
+        ++pt;
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      mbar_wait(&sh->a_ready, 0);
+      tc_fence_after();
+      const uint32_t idesc1 = umma_idesc_bf16(TILE_M, (uint32_t)HC);
+      const uint32_t idesc2 = umma_idesc_bf16(TILE_M, (uint32_t)TR);
+      const uint32_t a_addr = smem_u32(a_smem), hs_addr = smem_u32(hs_smem);
+      int t = 0;
+      auto gemm1 = [&](int j) {
+        const int buf = j & 1;
+        mbar_wait(&sh->hacc_empty[buf], (((uint32_t)j >> 1) & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t idesc1 = umma_idesc_bf16(TILE_M, (uint32_t)HC);
-        const uint32_t idesc2 = umma_idesc_bf16(TILE_M, (uint32_t)TR);
-        const uint32_t a_addr = smem_u32(a_smem), hs_addr = smem_u32(hs_smem);
-        int t = 0;
-        auto gemm1 = [&](int j) {
-          const int buf = j & 1;
-          mbar_wait(&sh->hacc_empty[buf], (((uint32_t)j >> 1) & 1u) ^ 1u);
+        const uint32_t d = tmem_base + (uint32_t)(hbase + buf * HC);
+        for (int kb = 0; kb < KB1; ++kb, ++t) {
+          const int s = t % p.stages;
+          mbar_wait(&sh->full[s], (uint32_t)(t / p.stages) & 1u);
           tc_fence_after();
-          const uint32_t d = tmem_base + (uint32_t)(hbase + buf * HC);
-          for (int kb = 0; kb < KB1; ++kb, ++t) {
+          const uint32_t b_addr = smem_u32(ring + s * stage_bytes);
+          const int steps = min(4, steps1 - kb * 4);
+          for (int k = 0; k < steps; ++k)
+            umma_bf16(d, umma_desc_sw128(a_addr + kb * A_KBLOCK_BYTES + k * 32), umma_desc_sw128(b_addr + k * 32),
+                      idesc1, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&sh->empty[s]);
+        }
+        umma_commit(&sh->hacc_full[buf]);
+      };
+      auto gemm2 = [&](int j) {
+        const int buf = j & 1;
+        mbar_wait(&sh->hs_full[buf], ((uint32_t)j >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t h_addr = hs_addr + buf * nkk * A_KBLOCK_BYTES;
+        for (int kk = 0; kk < nkk; ++kk) {
+          const int steps = min(4, steps2 - kk * 4);
+          for (int tt = 0; tt < nT; ++tt, ++t) {
             const int s = t % p.stages;
             mbar_wait(&sh->full[s], (uint32_t)(t / p.stages) & 1u);
             tc_fence_after();
             const uint32_t b_addr = smem_u32(ring + s * stage_bytes);
-            const int steps = min(4, steps1 - kb * 4);
             for (int k = 0; k < steps; ++k)
-              umma_bf16(d, umma_desc_sw128(a_addr + kb * A_KBLOCK_BYTES + k * 32), umma_desc_sw128(b_addr + k * 32),
-                        idesc1, (kb | k) != 0 ? 1u : 0u);
+              umma_bf16(tmem_base + (uint32_t)(tt * TR), umma_desc_sw128(h_addr + kk * A_KBLOCK_BYTES + k * 32),
+                        umma_desc_sw128(b_addr + k * 32), idesc2, (j | kk | k) != 0 ? 1u : 0u);
             umma_commit(&sh->empty[s]);
           }
-          umma_commit(&sh->hacc_full[buf]);
-        };
-        auto gemm2 = [&](int j) {
-          const int buf = j & 1;
-          mbar_wait(&sh->hs_full[buf], ((uint32_t)j >> 1) & 1u);
-          tc_fence_after();
-          const uint32_t h_addr = hs_addr + buf * nkk * A_KBLOCK_BYTES;
-          for (int kk = 0; kk < nkk; ++kk) {
-            const int steps = min(4, steps2 - kk * 4);
-            for (int tt = 0; tt < nT; ++tt, ++t) {
-              const int s = t % p.stages;
-              mbar_wait(&sh->full[s], (uint32_t)(t / p.stages) & 1u);
-              tc_fence_after();
-              const uint32_t b_addr = smem_u32(ring + s * stage_bytes);
-              for (int k = 0; k < steps; ++k)
-                umma_bf16(tmem_base + (uint32_t)(tt * TR), umma_desc_sw128(h_addr + kk * A_KBLOCK_BYTES + k * 32),
-                          umma_desc_sw128(b_addr + k * 32), idesc2, (j | kk | k) != 0 ? 1u : 0u);
-              umma_commit(&sh->empty[s]);
-            }
-          }
-          umma_commit(&sh->hs_empty[buf]);
-        };
-        gemm1(0);
-        for (int j = 0; j < nj; ++j) {
-          if (j + 1 < nj) gemm1(j + 1);
-          gemm2(j);
         }
-        umma_commit(&sh->y_full);
-      }
-    } else {
-      // ===== epilogue warps 2..5: thread <-> row =====
-      const int lg = warp & 3;
-      const int r = lg * 32 + lane;
-      const long long m = m0 + r;
-      const bool row_ok = m < p.M;
-      const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
-      float v[16];
+        umma_commit(&sh->hs_empty[buf]);
+      };
+      gemm1(0);
       for (int j = 0; j < nj; ++j) {
-        const int buf = j & 1;
-        const uint32_t ph = ((uint32_t)j >> 1) & 1u;
-        mbar_wait(&sh->hacc_full[buf], ph);
-        mbar_wait(&sh->hs_empty[buf], ph ^ 1u);
-        tc_fence_after();
-        uint8_t* hrow = hs_smem + buf * nkk * A_KBLOCK_BYTES;
-        const float* bj = b1s + j * HC;
-        for (int cb = 0; cb < steps2; ++cb) {
-          tmem_ld16(lane_addr + (uint32_t)(hbase + buf * HC + cb * 16), v);
-          tmem_ld_wait();
+        if (j + 1 < nj) gemm1(j + 1);
+        gemm2(j);
+      }
+      umma_commit(&sh->y_full);
+    }
+  } else {
+    // ===== epilogue warps 2..9: thread <-> row; the two warps of a lane group split the columns =====
+    const int lg = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int r = lg * 32 + lane;
+    const long long m = m0 + r;
+    const bool row_ok = m < p.M;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
+    // 16-column blocks of the hidden chunk owned by this warp
+    const int cb_beg = (steps2 & 1) ? (half ? steps2 : 0) : half * (steps2 >> 1);
+    const int cb_end = (steps2 & 1) ? steps2 : cb_beg + (steps2 >> 1);
+    float v[32];
+    for (int j = 0; j < nj; ++j) {
+      const int buf = j & 1;
+      const uint32_t ph = ((uint32_t)j >> 1) & 1u;
+      mbar_wait(&sh->hacc_full[buf], ph);
+      mbar_wait(&sh->hs_empty[buf], ph ^ 1u);
+      tc_fence_after();
+      uint8_t* hrow = hs_smem + buf * nkk * A_KBLOCK_BYTES;
+      const float* bj = b1s + j * HC;
+      const uint32_t t_chunk = lane_addr + (uint32_t)(hbase + buf * HC);
+      for (int cb = cb_beg; cb < cb_end; cb += 2) {
+        const bool two = cb + 1 < cb_end;
+        tmem_ld16(t_chunk + cb * 16, v);
+        if (two) tmem_ld16(t_chunk + cb * 16 + 16, v + 16);
+        tmem_ld_wait();
+#pragma unroll
+        for (int hb = 0; hb < 2; ++hb) {
+          if (hb == 1 && !two) break;
+          const int k = (cb + hb) * 16;
           uint32_t pk[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float a = gelu_erf(v[2 * i] + bj[cb * 16 + 2 * i]);
-            float b = gelu_erf(v[2 * i + 1] + bj[cb * 16 + 2 * i + 1]);
-            pk[i] = pack_bf16(a, b);
-          }
-          const int k = cb * 16;
+          for (int i = 0; i < 8; ++i)
+            pk[i] = pack_bf16(gelu_erf(v[hb * 16 + 2 * i] + bj[k + 2 * i]), gelu_erf(v[hb * 16 + 2 * i + 1] + bj[k + 2 * i + 1]));
           uint8_t* kb_base = hrow + (k >> 6) * A_KBLOCK_BYTES;
           *reinterpret_cast<uint4*>(kb_base + sw128_offset(r, k & 63)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           *reinterpret_cast<uint4*>(kb_base + sw128_offset(r, (k & 63) + 8)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         }
-        tc_fence_before();
-        fence_proxy_async();
-        mbar_arrive(&sh->hacc_empty[buf]);
-        mbar_arrive(&sh->hs_full[buf]);
       }
-      mbar_wait(&sh->y_full, 0);
-      tc_fence_after();
-      for (int cb = 0; cb < (C16 >> 4); ++cb) {
-        tmem_ld16(lane_addr + (uint32_t)(cb * 16), v);
-        tmem_ld_wait();
-        if (row_ok) {
+      tc_fence_before();
+      fence_proxy_async();
+      mbar_arrive(&sh->hacc_empty[buf]);
+      mbar_arrive(&sh->hs_full[buf]);
+    }
+    mbar_wait(&sh->y_full, 0);
+    tc_fence_after();
+    for (int cb = half; cb < (C16 >> 4); cb += 2) {
+      tmem_ld16(lane_addr + (uint32_t)(cb * 16), v);
+      tmem_ld_wait();
+      if (row_ok) {
 #pragma unroll
-          for (int j4 = 0; j4 < 16; j4 += 4) {
-            const int c = cb * 16 + j4;
-            if (c < C) {
-              const float4 xr = *reinterpret_cast<const float4*>(p.x + m * C + c);
-              float4 o;
-              o.x = v[j4 + 0] + b2s[c + 0] + xr.x;
-              o.y = v[j4 + 1] + b2s[c + 1] + xr.y;
-              o.z = v[j4 + 2] + b2s[c + 2] + xr.z;
-              o.w = v[j4 + 3] + b2s[c + 3] + xr.w;
-              *reinterpret_cast<float4*>(p.out + m * C + c) = o;
-            }
+        for (int j4 = 0; j4 < 16; j4 += 4) {
+          const int c = cb * 16 + j4;
+          if (c < C) {
+            const float4 xr = *reinterpret_cast<const float4*>(p.x + m * C + c);
+            float4 o;
+            o.x = v[j4 + 0] + b2s[c + 0] + xr.x;
+            o.y = v[j4 + 1] + b2s[c + 1] + xr.y;
+            o.z = v[j4 + 2] + b2s[c + 2] + xr.z;
+            o.w = v[j4 + 3] + b2s[c + 3] + xr.w;
+            *reinterpret_cast<float4*>(p.out + m * C + c) = o;
           }
         }
       }
@@ -272,21 +275,26 @@ int launch_mlp(MlpParams p, cudaStream_t stream) {
   p.tmem_cols = tc;
   const int stage_bytes = (p.HC > p.TR ? p.HC : p.TR) * 128;
   const int fixed = 1024 + (KB1 + 2 * nkk) * A_KBLOCK_BYTES + (4 * C + C16) * 4 + (int)sizeof(MlpSmem) + 64;
-  int stages = (232448 - fixed) / stage_bytes;
+  // aim for >= 2 co-resident CTAs per SM (smem <= ~113 KB, TMEM <= 256 columns) when >= 3 ring stages still fit
+  int stages = (tc <= 256) ? (113 * 1024 - fixed) / stage_bytes : 0;
+  if (stages < 3) stages = (232448 - fixed) / stage_bytes;
   if (stages > 6) stages = 6;
   SWN_CHECK(stages >= 2, "mlp: C=%d HC=%d TR=%d does not fit in shared memory", C, p.HC, p.TR);
   p.stages = stages;
   const size_t smem = (size_t)fixed + (size_t)stages * stage_bytes;
   const long long grid = ((long long)p.M + TILE_M - 1) / TILE_M;
-  const int KV = (C + 127) / 128;
   auto go = [&](auto kern) -> int {
     SWN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)grid, MLP_THREADS, smem, stream>>>(p);
     SWN_CUDA(cudaGetLastError());
     return 0;
   };
-  if (KV <= 1) return go(mlp_kernel<1>);
-  return go(mlp_kernel<3>);
+  if (C <= 16) return go(mlp_kernel<4, 1>);
+  if (C <= 32) return go(mlp_kernel<8, 1>);
+  if (C <= 64) return go(mlp_kernel<16, 1>);
+  if (C <= 128) return go(mlp_kernel<32, 1>);
+  if (C <= 256) return go(mlp_kernel<32, 2>);
+  return go(mlp_kernel<32, 3>);
 }
 
 }  // namespace swn
