@@ -23,6 +23,15 @@ static void mlp_config(int C, int* HC, int* TR) {
   else *HC = Hd;
   *TR = C16 <= 256 ? C16 : C16 / 2;
 }
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
 }  // namespace swn
 
 using namespace swn;
@@ -65,6 +74,7 @@ int swn_mlp(const float* x, float* out, int M, int C, const float* ln_w, const f
   p.x = x; p.out = out; p.M = M; p.C = C; p.ln_w = ln_w; p.ln_b = ln_b; p.ln_eps = ln_eps;
   p.Wp = reinterpret_cast<const __nv_bfloat16*>(Wp); p.b1 = b1; p.b2 = b2;
   mlp_config(C, &p.HC, &p.TR);
+  if (C <= 96) return launch_mlp_persist(p, num_sms(), reinterpret_cast<cudaStream_t>(stream));
   return launch_mlp(p, reinterpret_cast<cudaStream_t>(stream));
 }
 

@@ -52,8 +52,10 @@ struct MlpParams {
   int HC;                   // hidden chunk width
   int TR;                   // fc2 output rows per weight tile
   int stages, tmem_cols;    // filled in by the launcher
+  int row_stride;           // mlp_persist: staging row stride in bytes (filled in by the launcher)
 };
 int launch_mlp(MlpParams p, cudaStream_t stream);
+int launch_mlp_persist(MlpParams p, int num_sms, cudaStream_t stream);  // C <= 96: persistent, TMA-staged
 
 // ---- window_attn.cu -------------------------------------------------------------------------
 struct WinAttnParams {

@@ -1,0 +1,322 @@
+// Persistent, fully pipelined fused Swin MLP for channel widths C <= 96 (the token-heavy, HBM/epilogue-bound
+// layers):   out = x + fc2( GELU( fc1( LayerNorm(x) ) ) )      (SwinWNet.py:226-234,278)
+//
+// One CTA per SM loops over 128-row token tiles.  16 warps, specialised:
+//   warp 0  weight producer   pre-swizzled fc1/fc2 tiles -> smem ring            (cp.async.bulk + mbarrier)
+//   warp 2  input producer    fp32 rows of the NEXT tile -> padded smem staging  (cp.async.bulk per row; the
+//                             staged tile is both the LayerNorm input and the residual, read from HBM once)
+//   warps 4-7  LayerNorm      staging -> bf16 K-major SWIZZLE_128B A tile
+//   warp 1  MMA issuer        tcgen05.mma: Hacc = A W1_j^T (TMEM, double buffered), Y += Hs W2_j^T (TMEM)
+//   warps 8-15 epilogue       TMEM -> +b1, GELU -> bf16 Hs tile (smem, double buffered);  final: Y + b2 + residual
+//                             (staging) -> fp32 out
+// Every global load goes through the TMA engine one tile ahead of its use, so HBM latency is never exposed;
+// the hidden activation never leaves the SM.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace swn {
+
+constexpr int MP_WARPS = 16;
+constexpr int MP_THREADS = MP_WARPS * 32;
+constexpr int MP_LN_WARPS = 4;
+constexpr int MP_EPI_THREADS = 256;
+
+struct MpSmem {
+  uint64_t full[8], empty[8];
+  uint64_t in_full[2], in_empty[2];
+  uint64_t hacc_full[2], hacc_empty[2], hs_full[2], hs_empty[2];
+  uint64_t a_full, a_empty, y_full, y_empty;
+  uint32_t tmem_base;
+};
+
+template <int LPR>
+__global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+
+  const int C = p.C, C16 = (C + 15) & ~15;
+  const int KB1 = (C16 + 63) >> 6, steps1 = C16 >> 4;
+  const int HC = p.HC, TR = p.TR;
+  const int nj = (4 * C) / HC;
+  const int nkk = (HC + 63) >> 6, steps2 = HC >> 4;
+  const int nT = C16 / TR;
+  const int hbase = (C16 + 31) & ~31;
+  const int stage_bytes = max(HC, TR) * 128;
+  const int w1_bytes = HC * 128, w2_bytes = TR * 128;
+  const int rs = p.row_stride;  // staging row stride in bytes (odd number of 16-byte chunks)
+
+  uint8_t* a_smem = smem;
+  uint8_t* hs_smem = a_smem + KB1 * A_KBLOCK_BYTES;
+  uint8_t* ring = hs_smem + 2 * nkk * A_KBLOCK_BYTES;
+  uint8_t* stg = ring + p.stages * stage_bytes;                     // 2 x [128 x rs]
+  float* b1s = reinterpret_cast<float*>(stg + 2 * TILE_M * rs);     // [4C]
+  float* b2s = b1s + 4 * C;                                         // [C16]
+  float* lnw = b2s + C16;                                           // [C16]
+  float* lnb = lnw + C16;                                           // [C16]
+  MpSmem* sh = reinterpret_cast<MpSmem*>(lnb + C16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntiles = (p.M + TILE_M - 1) / TILE_M;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&sh->full[s], 1);
+      mbar_init(&sh->empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&sh->in_full[b], 1);
+      mbar_init(&sh->in_empty[b], MP_EPI_THREADS);
+      mbar_init(&sh->hacc_full[b], 1);
+      mbar_init(&sh->hacc_empty[b], MP_EPI_THREADS);
+      mbar_init(&sh->hs_full[b], MP_EPI_THREADS);
+      mbar_init(&sh->hs_empty[b], 1);
+    }
+    mbar_init(&sh->a_full, MP_LN_WARPS * 32);
+    mbar_init(&sh->a_empty, 1);
+    mbar_init(&sh->y_full, 1);
+    mbar_init(&sh->y_empty, MP_EPI_THREADS);
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < 4 * C; i += MP_THREADS) b1s[i] = p.b1[i];
+  for (int i = threadIdx.x; i < C16; i += MP_THREADS) {
+    b2s[i] = p.b2[i];
+    lnw[i] = i < C ? p.ln_w[i] : 0.f;
+    lnb[i] = i < C ? p.ln_b[i] : 0.f;
+  }
+  if (warp == 0) tmem_alloc(&sh->tmem_base, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sh->tmem_base;
+
+  if (warp == 0) {
+    // ===== weight producer: the whole fc1/fc2 stream once per tile =====
+    if (lane == 0) {
+      int t = 0;
+      auto push = [&](const uint8_t*& src, int bytes) {
+        const int s = t % p.stages;
+        mbar_wait(&sh->empty[s], ((uint32_t)(t / p.stages) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(&sh->full[s], (uint32_t)bytes);
+        bulk_g2s(ring + s * stage_bytes, src, (uint32_t)bytes, &sh->full[s]);
+        src += bytes;
+        ++t;
+      };
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.Wp);
+        for (int kb = 0; kb < KB1; ++kb) push(src, w1_bytes);
+        for (int j = 0; j < nj; ++j) {
+          if (j + 1 < nj)
+            for (int kb = 0; kb < KB1; ++kb) push(src, w1_bytes);
+          for (int i = 0; i < nkk * nT; ++i) push(src, w2_bytes);
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===== input producer: one bulk copy per token row into the padded staging tile =====
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int s = it & 1;
+      const long long m0 = (long long)tile * TILE_M;
+      const int rows = (int)min((long long)TILE_M, (long long)p.M - m0);
+      if (lane == 0) {
+        mbar_wait(&sh->in_empty[s], (((uint32_t)it >> 1) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(&sh->in_full[s], (uint32_t)(rows * C * 4));
+      }
+      __syncwarp();
+      uint8_t* dst = stg + s * TILE_M * rs;
+      for (int r = lane; r < rows; r += 32)
+        bulk_g2s(dst + r * rs, p.x + (m0 + r) * C, (uint32_t)(C * 4), &sh->in_full[s]);
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc1 = umma_idesc_bf16(TILE_M, (uint32_t)HC);
+      const uint32_t idesc2 = umma_idesc_bf16(TILE_M, (uint32_t)TR);
+      const uint32_t a_addr = smem_u32(a_smem), hs_addr = smem_u32(hs_smem);
+      int t = 0, it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int g0 = it * nj;  // global chunk counter of this tile's first chunk
+        auto gemm1 = [&](int j) {
+          const int g = g0 + j, buf = g & 1;
+          mbar_wait(&sh->hacc_empty[buf], (((uint32_t)g >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+          const uint32_t d = tmem_base + (uint32_t)(hbase + buf * HC);
+          for (int kb = 0; kb < KB1; ++kb, ++t) {
+            const int s = t % p.stages;
+            mbar_wait(&sh->full[s], (uint32_t)(t / p.stages) & 1u);
+            tc_fence_after();
+            const uint32_t b_addr = smem_u32(ring + s * stage_bytes);
+            const int steps = min(4, steps1 - kb * 4);
+            for (int k = 0; k < steps; ++k)
+              umma_bf16(d, umma_desc_sw128(a_addr + kb * A_KBLOCK_BYTES + k * 32), umma_desc_sw128(b_addr + k * 32),
+                        idesc1, (kb | k) != 0 ? 1u : 0u);
+            umma_commit(&sh->empty[s]);
+          }
+          umma_commit(&sh->hacc_full[buf]);
+          if (j == nj - 1) umma_commit(&sh->a_empty);  // A tile no longer needed once the last GEMM1 retires
+        };
+        auto gemm2 = [&](int j) {
+          const int g = g0 + j, buf = g & 1;
+          mbar_wait(&sh->hs_full[buf], ((uint32_t)g >> 1) & 1u);
+          if (j == 0) mbar_wait(&sh->y_empty, ((uint32_t)it & 1u) ^ 1u);  // previous tile's Y drained
+          tc_fence_after();
+          const uint32_t h_addr = hs_addr + buf * nkk * A_KBLOCK_BYTES;
+          for (int kk = 0; kk < nkk; ++kk) {
+            const int steps = min(4, steps2 - kk * 4);
+            for (int tt = 0; tt < nT; ++tt, ++t) {
+              const int s = t % p.stages;
+              mbar_wait(&sh->full[s], (uint32_t)(t / p.stages) & 1u);
+              tc_fence_after();
+              const uint32_t b_addr = smem_u32(ring + s * stage_bytes);
+              for (int k = 0; k < steps; ++k)
+                umma_bf16(tmem_base + (uint32_t)(tt * TR), umma_desc_sw128(h_addr + kk * A_KBLOCK_BYTES + k * 32),
+                          umma_desc_sw128(b_addr + k * 32), idesc2, (j | kk | k) != 0 ? 1u : 0u);
+              umma_commit(&sh->empty[s]);
+            }
+          }
+          umma_commit(&sh->hs_empty[buf]);
+        };
+        mbar_wait(&sh->a_full, (uint32_t)it & 1u);
+        tc_fence_after();
+        gemm1(0);
+        for (int j = 0; j < nj; ++j) {
+          if (j + 1 < nj) gemm1(j + 1);
+          gemm2(j);
+        }
+        umma_commit(&sh->y_full);
+      }
+    }
+  } else if (warp >= 4 && warp < 4 + MP_LN_WARPS) {
+    // ===== LayerNorm warps: staging (fp32) -> A tile (bf16, swizzled) =====
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int s = it & 1;
+      const long long m0 = (long long)tile * TILE_M;
+      const int rows = (int)min((long long)TILE_M, (long long)p.M - m0);
+      mbar_wait(&sh->in_full[s], ((uint32_t)it >> 1) & 1u);
+      mbar_wait(&sh->a_empty, ((uint32_t)it & 1u) ^ 1u);
+      const uint8_t* src = stg + s * TILE_M * rs;
+      build_a_tile<LPR, 1, 4, true>(a_smem, C, C16, lnw, lnb, p.ln_eps, warp - 4, MP_LN_WARPS, lane, [&](int r, int k) {
+        if (r >= rows) return make_float4(0.f, 0.f, 0.f, 0.f);
+        return *reinterpret_cast<const float4*>(src + r * rs + k * 4);
+      });
+      fence_proxy_async();
+      mbar_arrive(&sh->a_full);
+    }
+  } else if (warp >= 8) {
+    // ===== epilogue warps 8..15 =====
+    const int lg = warp & 3;
+    const int half = (warp - 8) >> 2;
+    const int r = lg * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
+    const int cb_beg = (steps2 & 1) ? (half ? steps2 : 0) : half * (steps2 >> 1);
+    const int cb_end = (steps2 & 1) ? steps2 : cb_beg + (steps2 >> 1);
+    float v[32];
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int s = it & 1;
+      const long long m = (long long)tile * TILE_M + r;
+      const bool row_ok = m < p.M;
+      for (int j = 0; j < nj; ++j) {
+        const int g = it * nj + j, buf = g & 1;
+        const uint32_t ph = ((uint32_t)g >> 1) & 1u;
+        mbar_wait(&sh->hacc_full[buf], ph);
+        mbar_wait(&sh->hs_empty[buf], ph ^ 1u);
+        tc_fence_after();
+        uint8_t* hrow = hs_smem + buf * nkk * A_KBLOCK_BYTES;
+        const float* bj = b1s + j * HC;
+        const uint32_t t_chunk = lane_addr + (uint32_t)(hbase + buf * HC);
+        for (int cb = cb_beg; cb < cb_end; cb += 2) {
+          const bool two = cb + 1 < cb_end;
+          tmem_ld16(t_chunk + cb * 16, v);
+          if (two) tmem_ld16(t_chunk + cb * 16 + 16, v + 16);
+          tmem_ld_wait();
+#pragma unroll
+          for (int hb = 0; hb < 2; ++hb) {
+            if (hb == 1 && !two) break;
+            const int k = (cb + hb) * 16;
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              pk[i] = pack_bf16(gelu_erf(v[hb * 16 + 2 * i] + bj[k + 2 * i]), gelu_erf(v[hb * 16 + 2 * i + 1] + bj[k + 2 * i + 1]));
+            uint8_t* kb_base = hrow + (k >> 6) * A_KBLOCK_BYTES;
+            *reinterpret_cast<uint4*>(kb_base + sw128_offset(r, k & 63)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(kb_base + sw128_offset(r, (k & 63) + 8)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+        }
+        tc_fence_before();
+        fence_proxy_async();
+        mbar_arrive(&sh->hacc_empty[buf]);
+        mbar_arrive(&sh->hs_full[buf]);
+      }
+      // final: Y + b2 + residual(staging) -> out
+      mbar_wait(&sh->y_full, (uint32_t)it & 1u);
+      tc_fence_after();
+      const uint8_t* res = stg + s * TILE_M * rs + r * rs;
+      for (int cb = half; cb < (C16 >> 4); cb += 2) {
+        tmem_ld16(lane_addr + (uint32_t)(cb * 16), v);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int j4 = 0; j4 < 16; j4 += 4) {
+            const int c = cb * 16 + j4;
+            if (c < C) {
+              const float4 xr = *reinterpret_cast<const float4*>(res + c * 4);
+              float4 o;
+              o.x = v[j4 + 0] + b2s[c + 0] + xr.x;
+              o.y = v[j4 + 1] + b2s[c + 1] + xr.y;
+              o.z = v[j4 + 2] + b2s[c + 2] + xr.z;
+              o.w = v[j4 + 3] + b2s[c + 3] + xr.w;
+              *reinterpret_cast<float4*>(p.out + m * C + c) = o;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&sh->y_empty);
+      mbar_arrive(&sh->in_empty[s]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+int launch_mlp_persist(MlpParams p, int num_sms, cudaStream_t stream) {
+  const int C = p.C, C16 = (C + 15) & ~15;
+  SWN_CHECK(p.M > 0 && C >= 4 && C % 4 == 0 && C <= 96, "mlp_persist: unsupported C=%d", C);
+  const int nj = (4 * C) / p.HC;
+  const int KB1 = (C16 + 63) >> 6, nkk = (p.HC + 63) >> 6;
+  int cols = ((C16 + 31) & ~31) + (nj > 1 ? 2 : 1) * p.HC, tc = 32;
+  while (tc < cols) tc <<= 1;
+  SWN_CHECK(tc <= 512, "mlp_persist: TMEM overflow");
+  p.tmem_cols = tc;
+  const int chunks = C / 4;
+  p.row_stride = (chunks + ((chunks & 1) ? 0 : 1)) * 16;
+  const int stage_bytes = (p.HC > p.TR ? p.HC : p.TR) * 128;
+  const int fixed = 1024 + (KB1 + 2 * nkk) * A_KBLOCK_BYTES + 2 * TILE_M * p.row_stride + (4 * C + 3 * C16) * 4 +
+                    (int)sizeof(MpSmem) + 64;
+  int stages = (232448 - fixed) / stage_bytes;
+  if (stages > 6) stages = 6;
+  SWN_CHECK(stages >= 2, "mlp_persist: does not fit in shared memory (C=%d)", C);
+  p.stages = stages;
+  const size_t smem = (size_t)fixed + (size_t)stages * stage_bytes;
+  const int ntiles = (p.M + TILE_M - 1) / TILE_M;
+  const int grid = ntiles < num_sms ? ntiles : num_sms;
+  auto go = [&](auto kern) -> int {
+    SWN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, MP_THREADS, smem, stream>>>(p);
+    SWN_CUDA(cudaGetLastError());
+    return 0;
+  };
+  if (C <= 16) return go(mlp_persist_kernel<4>);
+  if (C <= 32) return go(mlp_persist_kernel<8>);
+  if (C <= 64) return go(mlp_persist_kernel<16>);
+  return go(mlp_persist_kernel<32>);
+}
+
+}  // namespace swn

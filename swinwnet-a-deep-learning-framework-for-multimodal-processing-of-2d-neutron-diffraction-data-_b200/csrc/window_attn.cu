@@ -4,6 +4,12 @@
 // zero padding to a multiple of 5, torch.roll and compute_mask of the reference (SwinWNet.py:86-149,
 // 183-206, 246-272) are pure index math here: no window tensor is ever materialised.
 //
+// A CTA stages the q|k|v rows of a few windows in shared memory (25 tokens padded to 32 rows); each warp
+// then takes (window, head) pairs: S = Q K^T and O = P V run on the tensor cores (mma.sync m16n8k16 bf16,
+// fp32 accumulate; the 25x25 problem is far below a tcgen05 tile), softmax runs on the accumulator
+// fragments in fp32, O overwrites the pair's Q slot in shared memory and the CTA finally writes whole
+// token rows, coalesced.
+//
 // Padding semantics: the reference pads AFTER norm1, so a padded token is an exact zero vector whose
 // q/k/v equal the qkv bias; such tokens take part as keys and their outputs are dropped.
 // Shift semantics (shift>0, beyond what the reference can execute): standard Swin —
@@ -13,29 +19,40 @@
 
 namespace swn {
 
-constexpr int WA_THREADS = 256;
-constexpr int WS = 5, WN = 25;
+constexpr int WA_THREADS = 128;
+constexpr int WS = 5, WN = 25, WR = 32;  // window side, tokens per window, padded rows per window
+
+__device__ __forceinline__ void wa_mma(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void wa_ldsm_x2_trans(uint32_t& r0, uint32_t& r1, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
 
 template <int HD>
 __global__ void __launch_bounds__(WA_THREADS) window_attn_kernel(const WinAttnParams p, int nWy, int nWx, int wpb,
-                                                                  long long n_windows) {
-  extern __shared__ uint8_t smem_raw[];
+                                                                  long long n_windows, int RS) {
+  constexpr int KS = HD >= 16 ? HD / 16 : 1;   // k-steps of S = Q K^T
+  constexpr int NTO = HD >= 8 ? HD / 8 : 1;    // 8-wide output column tiles of O = P V
+  extern __shared__ __align__(16) uint8_t smem_raw[];
   const int C = p.C, nH = p.nH;
-  // smem: k,v as bf16 [wpb][25][2C] ; rel-pos table fp32 [81*nH] ; token index [wpb][25]
-  __nv_bfloat16* kv_s = reinterpret_cast<__nv_bfloat16*>(smem_raw);
-  float* tab_s = reinterpret_cast<float*>(smem_raw + (size_t)wpb * WN * 2 * C * sizeof(__nv_bfloat16));
-  long long* tok_s = reinterpret_cast<long long*>(tab_s + ((81 * nH + 1) & ~1));
-  int* rid_s = reinterpret_cast<int*>(tok_s + wpb * WN);
+  __nv_bfloat16* qkv_s = reinterpret_cast<__nv_bfloat16*>(smem_raw);                       // [wpb][32][RS]
+  float* tab_s = reinterpret_cast<float*>(smem_raw + (size_t)wpb * WR * RS * 2);          // [81*nH]
+  long long* tok_s = reinterpret_cast<long long*>(tab_s + ((81 * nH + 1) & ~1));         // [wpb][32]
+  int* rid_s = reinterpret_cast<int*>(tok_s + wpb * WR);                                  // [wpb][32]
 
   const long long w0 = (long long)blockIdx.x * wpb;
   for (int i = threadIdx.x; i < 81 * nH; i += WA_THREADS) tab_s[i] = p.rpb_table[i];
-  // token map: window-local slot -> global token row (or -1 for a padded slot), region id for the mask
-  for (int i = threadIdx.x; i < wpb * WN; i += WA_THREADS) {
-    const long long w = w0 + i / WN;
-    long long tok = -1;
+  for (int i = threadIdx.x; i < wpb * WR; i += WA_THREADS) {
+    const long long w = w0 + i / WR;
+    const int t = i % WR;
+    long long tok = -2;  // -2: padding row of the 32-row tile (zero), -1: padded token (takes the bias)
     int rid = 0;
-    if (w < n_windows) {
-      const int t = i % WN;
+    if (w < n_windows && t < WN) {
+      tok = -1;
       const int b = (int)(w / (nWy * nWx));
       const int wr = (int)(w - (long long)b * nWy * nWx);
       const int Y = (wr / nWx) * WS + t / WS, X = (wr % nWx) * WS + t % WS;
@@ -58,92 +75,161 @@ __global__ void __launch_bounds__(WA_THREADS) window_attn_kernel(const WinAttnPa
     rid_s[i] = rid;
   }
   __syncthreads();
-  // stage k|v (2C bf16 per token) ; padded slots take the bias
-  const int vec_per_tok = (2 * C) / 4;  // 8-byte vectors
-  for (int i = threadIdx.x; i < wpb * WN * vec_per_tok; i += WA_THREADS) {
-    const int slot = i / vec_per_tok, c4 = (i - slot * vec_per_tok) * 4;
+  // stage q|k|v (3C bf16 per token): 8-byte vectors, rows in window order
+  const int vpr = (3 * C) / 4;
+  for (int i = threadIdx.x; i < wpb * WR * vpr; i += WA_THREADS) {
+    const int slot = i / vpr, c4 = (i - slot * vpr) * 4;
     const long long tok = tok_s[slot];
-    uint2 val;
+    uint2 val = make_uint2(0u, 0u);
     if (tok >= 0) {
-      val = *reinterpret_cast<const uint2*>(p.qkv + tok * (3 * C) + C + c4);
-    } else {
-      const float4 bv = *reinterpret_cast<const float4*>(p.qkv_bias + C + c4);
+      val = __ldg(reinterpret_cast<const uint2*>(p.qkv + tok * (3 * C) + c4));
+    } else if (tok == -1) {
+      const float4 bv = *reinterpret_cast<const float4*>(p.qkv_bias + c4);
       val = make_uint2(pack_bf16(bv.x, bv.y), pack_bf16(bv.z, bv.w));
     }
-    *reinterpret_cast<uint2*>(kv_s + (size_t)slot * 2 * C + c4) = val;
+    *reinterpret_cast<uint2*>(qkv_s + (size_t)slot * RS + c4) = val;
   }
   __syncthreads();
 
-  const float scale = rsqrtf((float)HD);
-  const int pairs = wpb * nH * WN;
-  for (int pr = threadIdx.x; pr < pairs; pr += WA_THREADS) {
-    const int wl = pr / (nH * WN);
-    const int rem = pr - wl * nH * WN;
-    const int h = rem / WN, i = rem - h * WN;
-    const long long tok = tok_s[wl * WN + i];
-    if (tok < 0) continue;  // padded query: output dropped
-    float q[HD];
-    {
-      const __nv_bfloat16* qp = p.qkv + tok * (3 * C) + h * HD;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
+  const float sl2 = rsqrtf((float)HD) * 1.4426950408889634f;  // scores are kept in log2 units
+  // relative-position index = R[i] - R[j] + 40 with R[t] = (t/5)*9 + t%5
+  int Rrow[4], Rcol[8];
 #pragma unroll
-      for (int d = 0; d < HD; d += 4) {
-        const uint2 raw = *reinterpret_cast<const uint2*>(qp + d);
-        q[d] = bf16_lo(raw.x) * scale;
-        q[d + 1] = bf16_hi(raw.x) * scale;
-        q[d + 2] = bf16_lo(raw.y) * scale;
-        q[d + 3] = bf16_hi(raw.y) * scale;
+  for (int q = 0; q < 4; ++q) {
+    const int i = min((q >> 1) * 16 + g + (q & 1) * 8, WN - 1);
+    Rrow[q] = (i / WS) * 9 + i % WS + 40;
+  }
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int j = min((q >> 1) * 8 + t4 * 2 + (q & 1), WN - 1);
+    Rcol[q] = (j / WS) * 9 + j % WS;
+  }
+
+  for (int pr = warp; pr < wpb * nH; pr += WA_THREADS / 32) {
+    const int wl = pr / nH, h = pr - wl * nH;
+    if (w0 + wl >= n_windows) continue;
+    __nv_bfloat16* base = qkv_s + (size_t)wl * WR * RS;
+    const int qoff = h * HD, koff = C + h * HD, voff = 2 * C + h * HD;
+    // ---- S = Q K^T ----
+    float s[2][4][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) s[mt][nt][0] = s[mt][nt][1] = s[mt][nt][2] = s[mt][nt][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      const int col = ks * 16 + t4 * 2;
+      uint32_t a[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const __nv_bfloat16* qr = base + (mt * 16 + g) * RS + qoff + col;
+        a[mt][0] = col < HD ? *reinterpret_cast<const uint32_t*>(qr) : 0u;
+        a[mt][1] = col < HD ? *reinterpret_cast<const uint32_t*>(qr + 8 * RS) : 0u;
+        a[mt][2] = col + 8 < HD ? *reinterpret_cast<const uint32_t*>(qr + 8) : 0u;
+        a[mt][3] = col + 8 < HD ? *reinterpret_cast<const uint32_t*>(qr + 8 * RS + 8) : 0u;
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const __nv_bfloat16* kr = base + (nt * 8 + g) * RS + koff + col;
+        const uint32_t b0 = col < HD ? *reinterpret_cast<const uint32_t*>(kr) : 0u;
+        const uint32_t b1 = col + 8 < HD ? *reinterpret_cast<const uint32_t*>(kr + 8) : 0u;
+        wa_mma(s[0][nt], a[0], b0, b1);
+        wa_mma(s[1][nt], a[1], b0, b1);
       }
     }
-    const int yi = i / WS, xi = i % WS;
-    const int my_rid = rid_s[wl * WN + i];
-    const __nv_bfloat16* kbase = kv_s + (size_t)wl * WN * 2 * C + h * HD;
-    float s[WN];
-    float mx = -1e30f;
+    // ---- softmax over the 25 keys (fp32, log2 domain) ----
+    const int* rid = rid_s + wl * WR;
+    float inv[2][2];
 #pragma unroll
-    for (int j = 0; j < WN; ++j) {
-      const __nv_bfloat16* kp = kbase + (size_t)j * 2 * C;
-      float acc = 0.f;
+    for (int mt = 0; mt < 2; ++mt) {
+      float mx[2] = {-1e30f, -1e30f};
 #pragma unroll
-      for (int d = 0; d < HD; d += 4) {
-        const uint2 raw = *reinterpret_cast<const uint2*>(kp + d);
-        acc = fmaf(q[d], bf16_lo(raw.x), acc);
-        acc = fmaf(q[d + 1], bf16_hi(raw.x), acc);
-        acc = fmaf(q[d + 2], bf16_lo(raw.y), acc);
-        acc = fmaf(q[d + 3], bf16_hi(raw.y), acc);
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = nt * 8 + t4 * 2 + (e & 1);
+          const int qr = mt * 2 + (e >> 1);
+          float val = s[mt][nt][e] * sl2 + tab_s[(Rrow[qr] - Rcol[nt * 2 + (e & 1)]) * nH + h] * 1.4426950408889634f;
+          if (p.shift > 0) {
+            const int i = mt * 16 + g + (e >> 1) * 8;
+            if (rid[min(i, WR - 1)] != rid[j]) val -= 100.0f * 1.4426950408889634f;
+          }
+          val = j < WN ? val : -1e30f;
+          s[mt][nt][e] = val;
+          mx[e >> 1] = fmaxf(mx[e >> 1], val);
+        }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
       }
-      const int yj = j / WS, xj = j % WS;
-      acc += tab_s[((yi - yj + WS - 1) * (2 * WS - 1) + (xi - xj + WS - 1)) * nH + h];
-      if (p.shift > 0 && rid_s[wl * WN + j] != my_rid) acc -= 100.0f;
-      s[j] = acc;
-      mx = fmaxf(mx, acc);
-    }
-    float den = 0.f;
+      float sum[2] = {0.f, 0.f};
 #pragma unroll
-    for (int j = 0; j < WN; ++j) {
-      s[j] = __expf(s[j] - mx);
-      den += s[j];
-    }
-    const float inv = 1.0f / den;
-    float o[HD];
+      for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-    for (int d = 0; d < HD; ++d) o[d] = 0.f;
+        for (int e = 0; e < 4; ++e) {
+          const float pv = ex2_approx(s[mt][nt][e] - mx[e >> 1]);
+          s[mt][nt][e] = pv;
+          sum[e >> 1] += pv;
+        }
 #pragma unroll
-    for (int j = 0; j < WN; ++j) {
-      const __nv_bfloat16* vp = kbase + (size_t)j * 2 * C + C;
-      const float pj = s[j] * inv;
-#pragma unroll
-      for (int d = 0; d < HD; d += 4) {
-        const uint2 raw = *reinterpret_cast<const uint2*>(vp + d);
-        o[d] = fmaf(pj, bf16_lo(raw.x), o[d]);
-        o[d + 1] = fmaf(pj, bf16_hi(raw.x), o[d + 1]);
-        o[d + 2] = fmaf(pj, bf16_lo(raw.y), o[d + 2]);
-        o[d + 3] = fmaf(pj, bf16_hi(raw.y), o[d + 3]);
+      for (int r = 0; r < 2; ++r) {
+        sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 1);
+        sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 2);
+        inv[mt][r] = 1.0f / sum[r];
       }
     }
-    __nv_bfloat16* op = p.out + tok * C + h * HD;
+    // ---- O = P V ----
+    const int vcol0 = voff & ~7;          // 16-byte aligned column of the V tile (HD=4: head sits at +0 or +4)
+    float o[2][NTO][4];
 #pragma unroll
-    for (int d = 0; d < HD; d += 4)
-      *reinterpret_cast<uint2*>(op + d) = make_uint2(pack_bf16(o[d], o[d + 1]), pack_bf16(o[d + 2], o[d + 3]));
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int n = 0; n < NTO; ++n) o[mt][n][0] = o[mt][n][1] = o[mt][n][2] = o[mt][n][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      uint32_t pa[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        pa[mt][0] = pack_bf16(s[mt][2 * ks][0], s[mt][2 * ks][1]);
+        pa[mt][1] = pack_bf16(s[mt][2 * ks][2], s[mt][2 * ks][3]);
+        pa[mt][2] = pack_bf16(s[mt][2 * ks + 1][0], s[mt][2 * ks + 1][1]);
+        pa[mt][3] = pack_bf16(s[mt][2 * ks + 1][2], s[mt][2 * ks + 1][3]);
+      }
+      const uint32_t vrow = smem_u32(base + (ks * 16 + (lane & 15)) * RS + vcol0);
+#pragma unroll
+      for (int n = 0; n < NTO; ++n) {
+        uint32_t b0, b1;
+        wa_ldsm_x2_trans(b0, b1, vrow + n * 16);
+        wa_mma(o[0][n], pa[0], b0, b1);
+        wa_mma(o[1][n], pa[1], b0, b1);
+      }
+    }
+    // ---- O (normalised, bf16) overwrites this pair's Q slot ----
+    __syncwarp();
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int n = 0; n < NTO; ++n) {
+        const int dcol = n * 8 + t4 * 2 - (voff - vcol0);   // column inside the head
+        if (dcol >= 0 && dcol < HD) {
+          __nv_bfloat16* orow = base + (mt * 16 + g) * RS + qoff + dcol;
+          *reinterpret_cast<uint32_t*>(orow) = pack_bf16(o[mt][n][0] * inv[mt][0], o[mt][n][1] * inv[mt][0]);
+          *reinterpret_cast<uint32_t*>(orow + 8 * RS) = pack_bf16(o[mt][n][2] * inv[mt][1], o[mt][n][3] * inv[mt][1]);
+        }
+      }
+  }
+  __syncthreads();
+  // ---- write whole token rows (C bf16), coalesced ----
+  const int opr = C / 4;
+  for (int i = threadIdx.x; i < wpb * WN * opr; i += WA_THREADS) {
+    const int wl = i / (WN * opr);
+    const int rem = i - wl * WN * opr;
+    const int t = rem / opr, c4 = (rem - t * opr) * 4;
+    const long long tok = tok_s[wl * WR + t];
+    if (tok >= 0)
+      *reinterpret_cast<uint2*>(p.out + tok * C + c4) = *reinterpret_cast<const uint2*>(qkv_s + (size_t)(wl * WR + t) * RS + c4);
   }
 }
 
@@ -156,14 +242,17 @@ int launch_window_attn(WinAttnParams p, cudaStream_t stream) {
               "window_attn: shift>0 needs H,W multiples of the window size (reference semantics undefined otherwise)");
   const int nWy = (p.H + WS - 1) / WS, nWx = (p.W + WS - 1) / WS;
   const long long n_windows = (long long)p.B * nWy * nWx;
-  int wpb = WA_THREADS / (p.nH * WN);
+  int wpb = 12 / p.nH;
   if (wpb < 1) wpb = 1;
   if (wpb > 8) wpb = 8;
-  const size_t smem = (size_t)wpb * WN * 2 * p.C * 2 + (size_t)((81 * p.nH + 1) & ~1) * 4 + (size_t)wpb * WN * 12 + 16;
+  // padded row stride (bf16 elements): multiple of 8 (16-byte rows for ldmatrix), (RS/2) % 8 == 4 when possible
+  int RS = ((3 * p.C + 7) & ~7) + 8;
+  if (((RS / 2) & 7) == 0) RS += 8;
+  const size_t smem = (size_t)wpb * WR * RS * 2 + (size_t)((81 * p.nH + 1) & ~1) * 4 + (size_t)wpb * WR * 12 + 16;
   const long long grid = (n_windows + wpb - 1) / wpb;
   auto go = [&](auto kern) -> int {
     SWN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)grid, WA_THREADS, smem, stream>>>(p, nWy, nWx, wpb, n_windows);
+    kern<<<(unsigned)grid, WA_THREADS, smem, stream>>>(p, nWy, nWx, wpb, n_windows, RS);
     SWN_CUDA(cudaGetLastError());
     return 0;
   };
