@@ -63,6 +63,14 @@ int swn_rowgemm(const swn_rowgemm_args* args, void* stream);
 int swn_mlp(const float* x, float* out, int M, int C, const float* ln_w, const float* ln_b, float ln_eps,
             const void* Wp, const float* b1, const float* b2, void* stream);
 
+/* One whole SwinTransformerBlock (SwinWNet.py:236-280) for the narrow UpscalingHead layers, C in {12,24}, 3 heads,
+ * as a single fp32 kernel.  w[13] = device pointers to the block's parameters in nn.Module layout, in the order
+ * norm1.weight, norm1.bias, attn.qkv.weight [3C,C], attn.qkv.bias, attn.relative_position_bias_table [81,nH],
+ * attn.proj.weight [C,C], attn.proj.bias, norm2.weight, norm2.bias, mlp.0.weight [4C,C], mlp.0.bias,
+ * mlp.3.weight [C,4C], mlp.3.bias.  `w` itself is a HOST array.  out may alias x. */
+int swn_swin_block_small(const float* x, float* out, int B, int H, int W, int C, int num_heads, int shift, float eps,
+                         const float* const* w, void* stream);
+
 /* 5x5 (shifted-)window attention core on token-ordered qkv (SwinWNet.py:86-149,183-206,246-272). */
 int swn_window_attention(const void* qkv_bf16, void* out_bf16, const float* qkv_bias, const float* rpb_table,
                          int B, int H, int W, int C, int num_heads, int shift, void* stream);

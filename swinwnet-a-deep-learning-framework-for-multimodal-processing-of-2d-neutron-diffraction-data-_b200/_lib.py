@@ -32,6 +32,8 @@ SIGNATURES = {
     "swn_rowgemm": (c_int, [ctypes.POINTER(RowGemmArgs), c_void_p]),
     "swn_mlp": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
                         c_void_p]),
+    "swn_swin_block_small": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
+                                     ctypes.POINTER(c_void_p), c_void_p]),
     "swn_window_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                      c_void_p]),
     "swn_cross_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),

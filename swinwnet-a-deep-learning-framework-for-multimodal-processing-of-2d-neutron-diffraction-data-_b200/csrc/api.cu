@@ -63,6 +63,11 @@ int swn_rowgemm(const swn_rowgemm_args* a, void* stream) {
   SWN_CHECK(p.a_mode >= 0 && p.a_mode <= 3 && p.e_mode >= 0 && p.e_mode <= 2, "rowgemm: bad mode");
   if (p.a_mode == A_F32_LN || p.a_mode == A_MERGE_LN) SWN_CHECK(p.ln_w && p.ln_b, "rowgemm: LayerNorm params missing");
   if (p.e_mode == E_EXPAND) SWN_CHECK(p.ln2_w && p.ln2_b && p.nchunks == 4, "rowgemm: expand needs 4 chunks + LN params");
+  SWN_CHECK(p.M > 0 && p.K > 0 && p.K % 4 == 0 && p.NT >= 16 && p.NT <= 256 && p.NT % 16 == 0 && p.n_valid > 0 &&
+                p.n_valid <= p.NT && p.n_valid % 4 == 0 && p.nchunks >= 1 && p.ldo % 4 == 0,
+            "rowgemm: bad shape arguments");
+  const int rc = launch_rowgemm_persist(p, num_sms(), reinterpret_cast<cudaStream_t>(stream));
+  if (rc >= 0) return rc;
   return launch_rowgemm(p, reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -76,6 +81,15 @@ int swn_mlp(const float* x, float* out, int M, int C, const float* ln_w, const f
   mlp_config(C, &p.HC, &p.TR);
   if (C <= 96) return launch_mlp_persist(p, num_sms(), reinterpret_cast<cudaStream_t>(stream));
   return launch_mlp(p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int swn_swin_block_small(const float* x, float* out, int B, int H, int W, int C, int num_heads, int shift, float eps,
+                         const float* const* w, void* stream) {
+  SWN_CHECK(x && out && w, "swin_block_small: null pointer");
+  for (int i = 0; i < 13; ++i) SWN_CHECK(w[i] != nullptr, "swin_block_small: null parameter pointer %d", i);
+  SmallBlockParams p{x, out, B, H, W, C, num_heads, shift, eps,
+                     w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7], w[8], w[9], w[10], w[11], w[12]};
+  return launch_swin_block_small(p, num_sms(), reinterpret_cast<cudaStream_t>(stream));
 }
 
 int swn_window_attention(const void* qkv, void* out, const float* qkv_bias, const float* rpb_table, int B, int H, int W,

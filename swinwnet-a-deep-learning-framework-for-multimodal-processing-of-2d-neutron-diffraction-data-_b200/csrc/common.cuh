@@ -95,24 +95,27 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (or ~1 ms passes)
+// instead of spinning — spinning waiters were measured to eat ~45 % of the issue slots of the working warps.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u)
       : "memory");
   return ok != 0;
 }
 // Bounded wait: a protocol bug must surface as a trapped kernel (cudaErrorLaunchFailure), never as
-// a hung GPU.  ~4e9 cycles is seconds; every legitimate wait in these kernels is microseconds.
+// a hung GPU.  Every legitimate wait in these kernels is microseconds; the retry budget is seconds.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
+  const long long t0 = clock64();
+  uint32_t tries = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
+    if ((++tries & 63u) == 0 && clock64() - t0 > 8000000000LL) {
       printf("swn: mbarrier wait timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
       __trap();
     }
@@ -175,6 +178,30 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// One lane of a converged warp (deterministic for the full mask).  The MMA-issuing warps keep their loops
+// warp-uniform and predicate only the tcgen05 instructions on this: a loop under `if (lane == 0)` forces the
+// compiler through R2UR/vote sequences per descriptor and was measured to make the single issuing thread
+// (~150 cycles of scalar overhead per UMMA) the bottleneck of the whole CTA.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// ring-buffer cursor (stage index + phase parity) advanced without integer division
+struct RingPos {
+  int s;
+  uint32_t ph;
+  __device__ __forceinline__ void next(int stages) {
+    if (++s == stages) {
+      s = 0;
+      ph ^= 1u;
+    }
+  }
+};
 // arrive on `bar` once every previously issued tcgen05 op of this thread has completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -229,11 +256,11 @@ constexpr int A_KBLOCK_BYTES = TILE_M * 128;  // one [128 x 64] bf16 k-block
 template <int LPR, int KV, int UNR, bool LN, class Load>
 __device__ __forceinline__ void build_a_tile(uint8_t* a_smem, int K, int K16, const float* __restrict__ ln_w,
                                              const float* __restrict__ ln_b, float eps, int warp, int nwarps, int lane,
-                                             Load load) {
-  constexpr int RPW = 32 / LPR;          // rows per warp pass
+                                             Load load, int row_begin = 0, int row_end = TILE_M) {
+  constexpr int RPW = 32 / LPR;          // rows per warp pass (row_begin / row_end must be multiples of it)
   const int sub = lane / LPR, sl = lane % LPR;
   const float inv_k = 1.0f / (float)K;
-  for (int g0 = warp * UNR; g0 < TILE_M / RPW; g0 += nwarps * UNR) {
+  for (int g0 = row_begin / RPW + warp * UNR; g0 < row_end / RPW; g0 += nwarps * UNR) {
     float4 v[UNR][KV];
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
@@ -241,7 +268,7 @@ __device__ __forceinline__ void build_a_tile(uint8_t* a_smem, int K, int K16, co
 #pragma unroll
       for (int i = 0; i < KV; ++i) {
         const int k = (i * LPR + sl) * 4;
-        v[u][i] = (r < TILE_M && k < K) ? load(r, k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[u][i] = (r < row_end && k < K) ? load(r, k) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
     if (LN) {
@@ -292,7 +319,7 @@ __device__ __forceinline__ void build_a_tile(uint8_t* a_smem, int K, int K16, co
 #pragma unroll
       for (int i = 0; i < KV; ++i) {
         const int k = (i * LPR + sl) * 4;
-        if (r < TILE_M && k < K16) {
+        if (r < row_end && k < K16) {
           const uint2 o = (k < K) ? make_uint2(pack_bf16(v[u][i].x, v[u][i].y), pack_bf16(v[u][i].z, v[u][i].w))
                                   : make_uint2(0u, 0u);
           *reinterpret_cast<uint2*>(a_smem + (k >> 6) * A_KBLOCK_BYTES + sw128_offset(r, k & 63)) = o;

@@ -35,8 +35,12 @@ struct RowGemmParams {
   const float* ln2_b;
   // filled in by the launcher
   int stages, tmem_cols;
+  int stg_stride, pass_rows;  // cp.async input staging: padded row stride (bytes), rows per pass
+  int res_stride;             // residual staging row stride (bytes), 0 = residual read from global
 };
 int launch_rowgemm(RowGemmParams p, cudaStream_t stream);
+// persistent TMA-staged variant for narrow layers; returns -1 (no error) when the shape does not qualify
+int launch_rowgemm_persist(RowGemmParams p, int num_sms, cudaStream_t stream);
 
 // ---- mlp.cu ---------------------------------------------------------------------------------
 struct MlpParams {
@@ -66,6 +70,16 @@ struct WinAttnParams {
   int B, H, W, C, nH, shift;
 };
 int launch_window_attn(WinAttnParams p, cudaStream_t stream);
+
+// ---- small_block.cu -------------------------------------------------------------------------
+struct SmallBlockParams {   // one whole SwinTransformerBlock, C in {12, 24}, fp32 parameters in nn.Module layout
+  const float* x;
+  float* out;
+  int B, H, W, C, nH, shift;
+  float eps;
+  const float *n1w, *n1b, *Wqkv, *bqkv, *table, *Wp, *bp, *n2w, *n2b, *W1, *b1, *W2, *b2;
+};
+int launch_swin_block_small(SmallBlockParams p, int num_sms, cudaStream_t stream);
 
 // ---- cross_attn.cu --------------------------------------------------------------------------
 struct CrossAttnParams {

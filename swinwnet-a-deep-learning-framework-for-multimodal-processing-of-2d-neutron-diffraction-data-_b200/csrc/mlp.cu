@@ -135,58 +135,64 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(const MlpParams p) 
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      mbar_wait(&sh->a_ready, 0);
-      tc_fence_after();
-      const uint32_t idesc1 = umma_idesc_bf16(TILE_M, (uint32_t)HC);
-      const uint32_t idesc2 = umma_idesc_bf16(TILE_M, (uint32_t)TR);
-      const uint32_t a_addr = smem_u32(a_smem), hs_addr = smem_u32(hs_smem);
-      int t = 0;
-      auto gemm1 = [&](int j) {
-        const int buf = j & 1;
-        mbar_wait(&sh->hacc_empty[buf], (((uint32_t)j >> 1) & 1u) ^ 1u);
+    // ===== MMA issuer: warp-uniform loop, one elected lane issues tcgen05.mma / commit =====
+    mbar_wait(&sh->a_ready, 0);
+    const uint32_t idesc1 = umma_idesc_bf16(TILE_M, (uint32_t)HC);
+    const uint32_t idesc2 = umma_idesc_bf16(TILE_M, (uint32_t)TR);
+    const uint64_t a_desc0 = umma_desc_sw128(smem_u32(a_smem));
+    const uint64_t hs_desc0 = umma_desc_sw128(smem_u32(hs_smem));
+    const uint64_t ring_desc0 = umma_desc_sw128(smem_u32(ring));
+    const uint32_t stage_d16 = (uint32_t)(stage_bytes >> 4), kblk_d16 = A_KBLOCK_BYTES >> 4;
+    RingPos rp{0, 0u};
+    auto gemm1 = [&](int j) {
+      const int buf = j & 1;
+      mbar_wait(&sh->hacc_empty[buf], (((uint32_t)j >> 1) & 1u) ^ 1u);
+      const uint32_t d = tmem_base + (uint32_t)(hbase + buf * HC);
+      for (int kb = 0; kb < KB1; ++kb) {
+        mbar_wait(&sh->full[rp.s], rp.ph);
         tc_fence_after();
-        const uint32_t d = tmem_base + (uint32_t)(hbase + buf * HC);
-        for (int kb = 0; kb < KB1; ++kb, ++t) {
-          const int s = t % p.stages;
-          mbar_wait(&sh->full[s], (uint32_t)(t / p.stages) & 1u);
-          tc_fence_after();
-          const uint32_t b_addr = smem_u32(ring + s * stage_bytes);
+        if (elect_one()) {
+          const uint64_t ad = a_desc0 + (uint64_t)(kb * kblk_d16), bd = ring_desc0 + (uint64_t)(rp.s * stage_d16);
           const int steps = min(4, steps1 - kb * 4);
-          for (int k = 0; k < steps; ++k)
-            umma_bf16(d, umma_desc_sw128(a_addr + kb * A_KBLOCK_BYTES + k * 32), umma_desc_sw128(b_addr + k * 32),
-                      idesc1, (kb | k) != 0 ? 1u : 0u);
-          umma_commit(&sh->empty[s]);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (k < steps) umma_bf16(d, ad + 2 * k, bd + 2 * k, idesc1, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&sh->empty[rp.s]);
+          if (kb == KB1 - 1) umma_commit(&sh->hacc_full[buf]);
         }
-        umma_commit(&sh->hacc_full[buf]);
-      };
-      auto gemm2 = [&](int j) {
-        const int buf = j & 1;
-        mbar_wait(&sh->hs_full[buf], ((uint32_t)j >> 1) & 1u);
-        tc_fence_after();
-        const uint32_t h_addr = hs_addr + buf * nkk * A_KBLOCK_BYTES;
-        for (int kk = 0; kk < nkk; ++kk) {
-          const int steps = min(4, steps2 - kk * 4);
-          for (int tt = 0; tt < nT; ++tt, ++t) {
-            const int s = t % p.stages;
-            mbar_wait(&sh->full[s], (uint32_t)(t / p.stages) & 1u);
-            tc_fence_after();
-            const uint32_t b_addr = smem_u32(ring + s * stage_bytes);
-            for (int k = 0; k < steps; ++k)
-              umma_bf16(tmem_base + (uint32_t)(tt * TR), umma_desc_sw128(h_addr + kk * A_KBLOCK_BYTES + k * 32),
-                        umma_desc_sw128(b_addr + k * 32), idesc2, (j | kk | k) != 0 ? 1u : 0u);
-            umma_commit(&sh->empty[s]);
-          }
-        }
-        umma_commit(&sh->hs_empty[buf]);
-      };
-      gemm1(0);
-      for (int j = 0; j < nj; ++j) {
-        if (j + 1 < nj) gemm1(j + 1);
-        gemm2(j);
+        __syncwarp();
+        rp.next(p.stages);
       }
-      umma_commit(&sh->y_full);
+    };
+    auto gemm2 = [&](int j) {
+      const int buf = j & 1;
+      mbar_wait(&sh->hs_full[buf], ((uint32_t)j >> 1) & 1u);
+      const uint64_t hd0 = hs_desc0 + (uint64_t)(buf * nkk * kblk_d16);
+      for (int kk = 0; kk < nkk; ++kk) {
+        const int steps = min(4, steps2 - kk * 4);
+        for (int tt = 0; tt < nT; ++tt) {
+          mbar_wait(&sh->full[rp.s], rp.ph);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t ad = hd0 + (uint64_t)(kk * kblk_d16), bd = ring_desc0 + (uint64_t)(rp.s * stage_d16);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (k < steps) umma_bf16(tmem_base + (uint32_t)(tt * TR), ad + 2 * k, bd + 2 * k, idesc2, (j | kk | k) != 0 ? 1u : 0u);
+            umma_commit(&sh->empty[rp.s]);
+            if (kk == nkk - 1 && tt == nT - 1) {
+              umma_commit(&sh->hs_empty[buf]);
+              if (j == nj - 1) umma_commit(&sh->y_full);
+            }
+          }
+          __syncwarp();
+          rp.next(p.stages);
+        }
+      }
+    };
+    gemm1(0);
+    for (int j = 0; j < nj; ++j) {
+      if (j + 1 < nj) gemm1(j + 1);
+      gemm2(j);
     }
   } else {
     // ===== epilogue warps 2..9: thread <-> row; the two warps of a lane group split the columns =====
@@ -220,8 +226,11 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(const MlpParams p) 
           const int k = (cb + hb) * 16;
           uint32_t pk[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            pk[i] = pack_bf16(gelu_erf(v[hb * 16 + 2 * i] + bj[k + 2 * i]), gelu_erf(v[hb * 16 + 2 * i + 1] + bj[k + 2 * i + 1]));
+          for (int i = 0; i < 4; ++i) {
+            const float4 bb = *reinterpret_cast<const float4*>(bj + k + 4 * i);
+            pk[2 * i] = pack_bf16(gelu_erf(v[hb * 16 + 4 * i] + bb.x), gelu_erf(v[hb * 16 + 4 * i + 1] + bb.y));
+            pk[2 * i + 1] = pack_bf16(gelu_erf(v[hb * 16 + 4 * i + 2] + bb.z), gelu_erf(v[hb * 16 + 4 * i + 3] + bb.w));
+          }
           uint8_t* kb_base = hrow + (k >> 6) * A_KBLOCK_BYTES;
           *reinterpret_cast<uint4*>(kb_base + sw128_offset(r, k & 63)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           *reinterpret_cast<uint4*>(kb_base + sw128_offset(r, (k & 63) + 8)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);

@@ -93,14 +93,13 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
   if (warp == 0) {
     // ===== weight producer: the whole fc1/fc2 stream once per tile =====
     if (lane == 0) {
-      int t = 0;
+      RingPos rp{0, 0u};
       auto push = [&](const uint8_t*& src, int bytes) {
-        const int s = t % p.stages;
-        mbar_wait(&sh->empty[s], ((uint32_t)(t / p.stages) & 1u) ^ 1u);
-        mbar_arrive_expect_tx(&sh->full[s], (uint32_t)bytes);
-        bulk_g2s(ring + s * stage_bytes, src, (uint32_t)bytes, &sh->full[s]);
+        mbar_wait(&sh->empty[rp.s], rp.ph ^ 1u);
+        mbar_arrive_expect_tx(&sh->full[rp.s], (uint32_t)bytes);
+        bulk_g2s(ring + rp.s * stage_bytes, src, (uint32_t)bytes, &sh->full[rp.s]);
         src += bytes;
-        ++t;
+        rp.next(p.stages);
       };
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const uint8_t* src = reinterpret_cast<const uint8_t*>(p.Wp);
@@ -129,62 +128,71 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
         bulk_g2s(dst + r * rs, p.x + (m0 + r) * C, (uint32_t)(C * 4), &sh->in_full[s]);
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      const uint32_t idesc1 = umma_idesc_bf16(TILE_M, (uint32_t)HC);
-      const uint32_t idesc2 = umma_idesc_bf16(TILE_M, (uint32_t)TR);
-      const uint32_t a_addr = smem_u32(a_smem), hs_addr = smem_u32(hs_smem);
-      int t = 0, it = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-        const int g0 = it * nj;  // global chunk counter of this tile's first chunk
-        auto gemm1 = [&](int j) {
-          const int g = g0 + j, buf = g & 1;
-          mbar_wait(&sh->hacc_empty[buf], (((uint32_t)g >> 1) & 1u) ^ 1u);
+    // ===== MMA issuer: warp-uniform loop, one elected lane issues tcgen05.mma / commit =====
+    const uint32_t idesc1 = umma_idesc_bf16(TILE_M, (uint32_t)HC);
+    const uint32_t idesc2 = umma_idesc_bf16(TILE_M, (uint32_t)TR);
+    const uint64_t a_desc0 = umma_desc_sw128(smem_u32(a_smem));
+    const uint64_t hs_desc0 = umma_desc_sw128(smem_u32(hs_smem));
+    const uint64_t ring_desc0 = umma_desc_sw128(smem_u32(ring));
+    const uint32_t stage_d16 = (uint32_t)(stage_bytes >> 4), kblk_d16 = A_KBLOCK_BYTES >> 4;
+    RingPos rp{0, 0u};
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int g0 = it * nj;  // global chunk counter of this tile's first chunk
+      auto gemm1 = [&](int j) {
+        const int g = g0 + j, buf = g & 1;
+        mbar_wait(&sh->hacc_empty[buf], (((uint32_t)g >> 1) & 1u) ^ 1u);
+        const uint32_t d = tmem_base + (uint32_t)(hbase + buf * HC);
+        for (int kb = 0; kb < KB1; ++kb) {
+          mbar_wait(&sh->full[rp.s], rp.ph);
           tc_fence_after();
-          const uint32_t d = tmem_base + (uint32_t)(hbase + buf * HC);
-          for (int kb = 0; kb < KB1; ++kb, ++t) {
-            const int s = t % p.stages;
-            mbar_wait(&sh->full[s], (uint32_t)(t / p.stages) & 1u);
-            tc_fence_after();
-            const uint32_t b_addr = smem_u32(ring + s * stage_bytes);
+          if (elect_one()) {
+            const uint64_t ad = a_desc0 + (uint64_t)(kb * kblk_d16), bd = ring_desc0 + (uint64_t)(rp.s * stage_d16);
             const int steps = min(4, steps1 - kb * 4);
-            for (int k = 0; k < steps; ++k)
-              umma_bf16(d, umma_desc_sw128(a_addr + kb * A_KBLOCK_BYTES + k * 32), umma_desc_sw128(b_addr + k * 32),
-                        idesc1, (kb | k) != 0 ? 1u : 0u);
-            umma_commit(&sh->empty[s]);
-          }
-          umma_commit(&sh->hacc_full[buf]);
-          if (j == nj - 1) umma_commit(&sh->a_empty);  // A tile no longer needed once the last GEMM1 retires
-        };
-        auto gemm2 = [&](int j) {
-          const int g = g0 + j, buf = g & 1;
-          mbar_wait(&sh->hs_full[buf], ((uint32_t)g >> 1) & 1u);
-          if (j == 0) mbar_wait(&sh->y_empty, ((uint32_t)it & 1u) ^ 1u);  // previous tile's Y drained
-          tc_fence_after();
-          const uint32_t h_addr = hs_addr + buf * nkk * A_KBLOCK_BYTES;
-          for (int kk = 0; kk < nkk; ++kk) {
-            const int steps = min(4, steps2 - kk * 4);
-            for (int tt = 0; tt < nT; ++tt, ++t) {
-              const int s = t % p.stages;
-              mbar_wait(&sh->full[s], (uint32_t)(t / p.stages) & 1u);
-              tc_fence_after();
-              const uint32_t b_addr = smem_u32(ring + s * stage_bytes);
-              for (int k = 0; k < steps; ++k)
-                umma_bf16(tmem_base + (uint32_t)(tt * TR), umma_desc_sw128(h_addr + kk * A_KBLOCK_BYTES + k * 32),
-                          umma_desc_sw128(b_addr + k * 32), idesc2, (j | kk | k) != 0 ? 1u : 0u);
-              umma_commit(&sh->empty[s]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (k < steps) umma_bf16(d, ad + 2 * k, bd + 2 * k, idesc1, (kb | k) != 0 ? 1u : 0u);
+            umma_commit(&sh->empty[rp.s]);
+            if (kb == KB1 - 1) {
+              umma_commit(&sh->hacc_full[buf]);
+              if (j == nj - 1) umma_commit(&sh->a_empty);  // A tile free once the last GEMM1 retires
             }
           }
-          umma_commit(&sh->hs_empty[buf]);
-        };
-        mbar_wait(&sh->a_full, (uint32_t)it & 1u);
-        tc_fence_after();
-        gemm1(0);
-        for (int j = 0; j < nj; ++j) {
-          if (j + 1 < nj) gemm1(j + 1);
-          gemm2(j);
+          __syncwarp();
+          rp.next(p.stages);
         }
-        umma_commit(&sh->y_full);
+      };
+      auto gemm2 = [&](int j) {
+        const int g = g0 + j, buf = g & 1;
+        mbar_wait(&sh->hs_full[buf], ((uint32_t)g >> 1) & 1u);
+        if (j == 0) mbar_wait(&sh->y_empty, ((uint32_t)it & 1u) ^ 1u);  // previous tile's Y drained
+        const uint64_t hd0 = hs_desc0 + (uint64_t)(buf * nkk * kblk_d16);
+        for (int kk = 0; kk < nkk; ++kk) {
+          const int steps = min(4, steps2 - kk * 4);
+          for (int tt = 0; tt < nT; ++tt) {
+            mbar_wait(&sh->full[rp.s], rp.ph);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint64_t ad = hd0 + (uint64_t)(kk * kblk_d16), bd = ring_desc0 + (uint64_t)(rp.s * stage_d16);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (k < steps) umma_bf16(tmem_base + (uint32_t)(tt * TR), ad + 2 * k, bd + 2 * k, idesc2, (j | kk | k) != 0 ? 1u : 0u);
+              umma_commit(&sh->empty[rp.s]);
+              if (kk == nkk - 1 && tt == nT - 1) {
+                umma_commit(&sh->hs_empty[buf]);
+                if (j == nj - 1) umma_commit(&sh->y_full);
+              }
+            }
+            __syncwarp();
+            rp.next(p.stages);
+          }
+        }
+      };
+      mbar_wait(&sh->a_full, (uint32_t)it & 1u);
+      gemm1(0);
+      for (int j = 0; j < nj; ++j) {
+        if (j + 1 < nj) gemm1(j + 1);
+        gemm2(j);
       }
     }
   } else if (warp >= 4 && warp < 4 + MP_LN_WARPS) {
@@ -196,11 +204,51 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
       const int rows = (int)min((long long)TILE_M, (long long)p.M - m0);
       mbar_wait(&sh->in_full[s], ((uint32_t)it >> 1) & 1u);
       mbar_wait(&sh->a_empty, ((uint32_t)it & 1u) ^ 1u);
-      const uint8_t* src = stg + s * TILE_M * rs;
-      build_a_tile<LPR, 1, 4, true>(a_smem, C, C16, lnw, lnb, p.ln_eps, warp - 4, MP_LN_WARPS, lane, [&](int r, int k) {
-        if (r >= rows) return make_float4(0.f, 0.f, 0.f, 0.f);
-        return *reinterpret_cast<const float4*>(src + r * rs + k * 4);
-      });
+      // one thread per row (the staging rows are padded to an odd number of 16-byte chunks, so this is bank
+      // conflict free): no shuffles, long independent instruction streams.  Shifted one-pass moments.
+      const int row = (warp - 4) * 32 + lane;
+      const uint8_t* src = stg + s * TILE_M * rs + row * rs;
+      const bool row_ok = row < rows;
+      float mean = 0.f, rstd = 0.f;
+      if (row_ok) {
+        const float x0 = *reinterpret_cast<const float*>(src);
+        float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int c4 = 0; c4 < C / 4; ++c4) {
+          const float4 v = *reinterpret_cast<const float4*>(src + c4 * 16);
+          const float d0 = v.x - x0, d1 = v.y - x0, d2 = v.z - x0, d3 = v.w - x0;
+          s1[0] += d0; s1[1] += d1; s1[2] += d2; s1[3] += d3;
+          s2[0] = fmaf(d0, d0, s2[0]); s2[1] = fmaf(d1, d1, s2[1]); s2[2] = fmaf(d2, d2, s2[2]); s2[3] = fmaf(d3, d3, s2[3]);
+        }
+        const float inv_c = 1.0f / (float)C;
+        const float m1 = ((s1[0] + s1[1]) + (s1[2] + s1[3])) * inv_c;
+        const float m2 = ((s2[0] + s2[1]) + (s2[2] + s2[3])) * inv_c;
+        mean = x0 + m1;
+        rstd = rsqrtf(fmaxf(m2 - m1 * m1, 0.f) + p.ln_eps);
+      }
+      for (int k = 0; k < C16; k += 8) {  // one 16-byte bf16 chunk of the A tile per step
+        uint32_t pk[4] = {0u, 0u, 0u, 0u};
+        if (row_ok && k < C) {
+          float y[8];
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int kk = k + hh * 4;
+            if (kk < C) {
+              const float4 v = *reinterpret_cast<const float4*>(src + kk * 4);
+              const float4 gw = *reinterpret_cast<const float4*>(lnw + kk);
+              const float4 gb = *reinterpret_cast<const float4*>(lnb + kk);
+              y[hh * 4 + 0] = fmaf((v.x - mean) * rstd, gw.x, gb.x);
+              y[hh * 4 + 1] = fmaf((v.y - mean) * rstd, gw.y, gb.y);
+              y[hh * 4 + 2] = fmaf((v.z - mean) * rstd, gw.z, gb.z);
+              y[hh * 4 + 3] = fmaf((v.w - mean) * rstd, gw.w, gb.w);
+            } else {
+              y[hh * 4 + 0] = y[hh * 4 + 1] = y[hh * 4 + 2] = y[hh * 4 + 3] = 0.f;
+            }
+          }
+          pk[0] = pack_bf16(y[0], y[1]); pk[1] = pack_bf16(y[2], y[3]);
+          pk[2] = pack_bf16(y[4], y[5]); pk[3] = pack_bf16(y[6], y[7]);
+        }
+        *reinterpret_cast<uint4*>(a_smem + (k >> 6) * A_KBLOCK_BYTES + sw128_offset(row, k & 63)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
       fence_proxy_async();
       mbar_arrive(&sh->a_full);
     }
@@ -238,8 +286,11 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
             const int k = (cb + hb) * 16;
             uint32_t pk[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              pk[i] = pack_bf16(gelu_erf(v[hb * 16 + 2 * i] + bj[k + 2 * i]), gelu_erf(v[hb * 16 + 2 * i + 1] + bj[k + 2 * i + 1]));
+            for (int i = 0; i < 4; ++i) {
+              const float4 bb = *reinterpret_cast<const float4*>(bj + k + 4 * i);
+              pk[2 * i] = pack_bf16(gelu_erf(v[hb * 16 + 4 * i] + bb.x), gelu_erf(v[hb * 16 + 4 * i + 1] + bb.y));
+              pk[2 * i + 1] = pack_bf16(gelu_erf(v[hb * 16 + 4 * i + 2] + bb.z), gelu_erf(v[hb * 16 + 4 * i + 3] + bb.w));
+            }
             uint8_t* kb_base = hrow + (k >> 6) * A_KBLOCK_BYTES;
             *reinterpret_cast<uint4*>(kb_base + sw128_offset(r, k & 63)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             *reinterpret_cast<uint4*>(kb_base + sw128_offset(r, (k & 63) + 8)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);

@@ -133,30 +133,31 @@ __global__ void __launch_bounds__(RG_THREADS, 1) rowgemm_kernel(const RowGemmPar
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      mbar_wait(&sh->a_ready, 0);
-      tc_fence_after();
-      const uint32_t idesc = umma_idesc_bf16(TILE_M, (uint32_t)p.NT);
-      const uint32_t a_addr = smem_u32(a_smem);
-      int t = 0;
-      for (int n = 0; n < p.nchunks; ++n) {
-        const int buf = n & 1;
-        mbar_wait(&sh->tmem_empty[buf], (((uint32_t)n >> 1) & 1u) ^ 1u);
+    // ===== MMA issuer: warp-uniform loop, one elected lane issues tcgen05.mma / commit =====
+    mbar_wait(&sh->a_ready, 0);
+    const uint32_t idesc = umma_idesc_bf16(TILE_M, (uint32_t)p.NT);
+    const uint64_t a_desc0 = umma_desc_sw128(smem_u32(a_smem));
+    const uint64_t ring_desc0 = umma_desc_sw128(smem_u32(ring));
+    const uint32_t stage_d16 = (uint32_t)(stage_bytes >> 4), kblk_d16 = A_KBLOCK_BYTES >> 4;
+    RingPos rp{0, 0u};
+    for (int n = 0; n < p.nchunks; ++n) {
+      const int buf = n & 1;
+      mbar_wait(&sh->tmem_empty[buf], (((uint32_t)n >> 1) & 1u) ^ 1u);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * nt32);
+      for (int kb = 0; kb < KB; ++kb) {
+        mbar_wait(&sh->full[rp.s], rp.ph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * nt32);
-        for (int kb = 0; kb < KB; ++kb, ++t) {
-          const int s = t % p.stages;
-          mbar_wait(&sh->full[s], (uint32_t)(t / p.stages) & 1u);
-          tc_fence_after();
-          const uint32_t b_addr = smem_u32(ring + s * stage_bytes);
+        if (elect_one()) {
+          const uint64_t ad = a_desc0 + (uint64_t)(kb * kblk_d16), bd = ring_desc0 + (uint64_t)(rp.s * stage_d16);
           const int steps = min(4, ksteps_total - kb * 4);
-          for (int k = 0; k < steps; ++k)
-            umma_bf16(d_tmem, umma_desc_sw128(a_addr + kb * A_KBLOCK_BYTES + k * 32), umma_desc_sw128(b_addr + k * 32),
-                      idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit(&sh->empty[s]);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (k < steps) umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&sh->empty[rp.s]);
+          if (kb == KB - 1) umma_commit(&sh->tmem_full[buf]);
         }
-        umma_commit(&sh->tmem_full[buf]);
+        __syncwarp();
+        rp.next(p.stages);
       }
     }
   } else {

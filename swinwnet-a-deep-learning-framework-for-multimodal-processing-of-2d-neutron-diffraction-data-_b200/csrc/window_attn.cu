@@ -45,7 +45,8 @@ __global__ void __launch_bounds__(WA_THREADS) window_attn_kernel(const WinAttnPa
   int* rid_s = reinterpret_cast<int*>(tok_s + wpb * WR);                                  // [wpb][32]
 
   const long long w0 = (long long)blockIdx.x * wpb;
-  for (int i = threadIdx.x; i < 81 * nH; i += WA_THREADS) tab_s[i] = p.rpb_table[i];
+  // relative-position table, transposed to [head][81] and pre-scaled into the log2 domain
+  for (int i = threadIdx.x; i < 81 * nH; i += WA_THREADS) tab_s[i] = p.rpb_table[(i % 81) * nH + i / 81] * 1.4426950408889634f;
   for (int i = threadIdx.x; i < wpb * WR; i += WA_THREADS) {
     const long long w = w0 + i / WR;
     const int t = i % WR;
@@ -75,23 +76,36 @@ __global__ void __launch_bounds__(WA_THREADS) window_attn_kernel(const WinAttnPa
     rid_s[i] = rid;
   }
   __syncthreads();
-  // stage q|k|v (3C bf16 per token): 8-byte vectors, rows in window order
-  const int vpr = (3 * C) / 4;
-  for (int i = threadIdx.x; i < wpb * WR * vpr; i += WA_THREADS) {
-    const int slot = i / vpr, c4 = (i - slot * vpr) * 4;
+  // stage q|k|v (3C bf16 per token), rows in window order: one warp per row, lanes along the row
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
+  const bool vec8 = (3 * C) % 8 == 0;  // 16-byte vectors when the row length allows
+  for (int slot = warp; slot < wpb * WR; slot += WA_THREADS / 32) {
     const long long tok = tok_s[slot];
-    uint2 val = make_uint2(0u, 0u);
+    __nv_bfloat16* dst = qkv_s + (size_t)slot * RS;
     if (tok >= 0) {
-      val = __ldg(reinterpret_cast<const uint2*>(p.qkv + tok * (3 * C) + c4));
-    } else if (tok == -1) {
-      const float4 bv = *reinterpret_cast<const float4*>(p.qkv_bias + c4);
-      val = make_uint2(pack_bf16(bv.x, bv.y), pack_bf16(bv.z, bv.w));
+      const __nv_bfloat16* src = p.qkv + tok * (3 * C);
+      // cp.async: every row of the CTA is in flight at once, so DRAM latency is paid once per CTA
+      if (vec8) {
+        for (int c = lane * 8; c < 3 * C; c += 256)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + c)), "l"(src + c) : "memory");
+      } else {
+        for (int c = lane * 4; c < 3 * C; c += 128)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst + c)), "l"(src + c) : "memory");
+      }
+    } else {
+      for (int c = lane * 4; c < 3 * C; c += 128) {
+        uint2 val = make_uint2(0u, 0u);
+        if (tok == -1) {
+          const float4 bv = *reinterpret_cast<const float4*>(p.qkv_bias + c);
+          val = make_uint2(pack_bf16(bv.x, bv.y), pack_bf16(bv.z, bv.w));
+        }
+        *reinterpret_cast<uint2*>(dst + c) = val;
+      }
     }
-    *reinterpret_cast<uint2*>(qkv_s + (size_t)slot * RS + c4) = val;
   }
+  asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
   const float sl2 = rsqrtf((float)HD) * 1.4426950408889634f;  // scores are kept in log2 units
   // relative-position index = R[i] - R[j] + 40 with R[t] = (t/5)*9 + t%5
   int Rrow[4], Rcol[8];
@@ -140,6 +154,7 @@ __global__ void __launch_bounds__(WA_THREADS) window_attn_kernel(const WinAttnPa
     }
     // ---- softmax over the 25 keys (fp32, log2 domain) ----
     const int* rid = rid_s + wl * WR;
+    const float* tabh = tab_s + h * 81;
     float inv[2][2];
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt) {
@@ -150,12 +165,12 @@ __global__ void __launch_bounds__(WA_THREADS) window_attn_kernel(const WinAttnPa
         for (int e = 0; e < 4; ++e) {
           const int j = nt * 8 + t4 * 2 + (e & 1);
           const int qr = mt * 2 + (e >> 1);
-          float val = s[mt][nt][e] * sl2 + tab_s[(Rrow[qr] - Rcol[nt * 2 + (e & 1)]) * nH + h] * 1.4426950408889634f;
+          float val = fmaf(s[mt][nt][e], sl2, tabh[Rrow[qr] - Rcol[nt * 2 + (e & 1)]]);
           if (p.shift > 0) {
             const int i = mt * 16 + g + (e >> 1) * 8;
             if (rid[min(i, WR - 1)] != rid[j]) val -= 100.0f * 1.4426950408889634f;
           }
-          val = j < WN ? val : -1e30f;
+          if (nt == 3) val = j < WN ? val : -1e30f;   // keys 25..31 are padding (only the last 8-key tile)
           s[mt][nt][e] = val;
           mx[e >> 1] = fmaxf(mx[e >> 1], val);
         }
@@ -222,14 +237,17 @@ __global__ void __launch_bounds__(WA_THREADS) window_attn_kernel(const WinAttnPa
   }
   __syncthreads();
   // ---- write whole token rows (C bf16), coalesced ----
-  const int opr = C / 4;
-  for (int i = threadIdx.x; i < wpb * WN * opr; i += WA_THREADS) {
-    const int wl = i / (WN * opr);
-    const int rem = i - wl * WN * opr;
-    const int t = rem / opr, c4 = (rem - t * opr) * 4;
+  for (int i = warp; i < wpb * WN; i += WA_THREADS / 32) {
+    const int wl = i / WN, t = i - wl * WN;
     const long long tok = tok_s[wl * WR + t];
-    if (tok >= 0)
-      *reinterpret_cast<uint2*>(p.out + tok * C + c4) = *reinterpret_cast<const uint2*>(qkv_s + (size_t)(wl * WR + t) * RS + c4);
+    if (tok < 0) continue;
+    const __nv_bfloat16* src = qkv_s + (size_t)(wl * WR + t) * RS;
+    __nv_bfloat16* dst = p.out + tok * C;
+    if (C % 8 == 0) {
+      for (int c = lane * 8; c < C; c += 256) *reinterpret_cast<uint4*>(dst + c) = *reinterpret_cast<const uint4*>(src + c);
+    } else {
+      for (int c = lane * 4; c < C; c += 128) *reinterpret_cast<uint2*>(dst + c) = *reinterpret_cast<const uint2*>(src + c);
+    }
   }
 }
 
@@ -242,12 +260,15 @@ int launch_window_attn(WinAttnParams p, cudaStream_t stream) {
               "window_attn: shift>0 needs H,W multiples of the window size (reference semantics undefined otherwise)");
   const int nWy = (p.H + WS - 1) / WS, nWx = (p.W + WS - 1) / WS;
   const long long n_windows = (long long)p.B * nWy * nWx;
-  int wpb = 12 / p.nH;
-  if (wpb < 1) wpb = 1;
-  if (wpb > 8) wpb = 8;
   // padded row stride (bf16 elements): multiple of 8 (16-byte rows for ldmatrix), (RS/2) % 8 == 4 when possible
   int RS = ((3 * p.C + 7) & ~7) + 8;
   if (((RS / 2) & 7) == 0) RS += 8;
+  // windows per CTA: enough (window, head) pairs for the 4 warps, but at most ~44 KB of staging so that >= 4 CTAs
+  // (16+ warps) are resident per SM
+  int wpb = 12 / p.nH;
+  if (wpb < 1) wpb = 1;
+  if (wpb > 8) wpb = 8;
+  while (wpb > 1 && wpb * WR * RS * 2 > 44 * 1024) --wpb;
   const size_t smem = (size_t)wpb * WR * RS * 2 + (size_t)((81 * p.nH + 1) & ~1) * 4 + (size_t)wpb * WR * 12 + 16;
   const long long grid = (n_windows + wpb - 1) / wpb;
   auto go = [&](auto kern) -> int {

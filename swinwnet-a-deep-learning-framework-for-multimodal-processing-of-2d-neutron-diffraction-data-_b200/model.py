@@ -144,6 +144,16 @@ class SwinTransformerBlock(nn.Module):
         B, L, C = x.shape
         H, W = resolution
         assert L == H * W, "input feature has wrong size"
+        if C in (12, 24) and self.num_heads == 3 and self.window_size == WINDOW and int(C * self.mlp_ratio) == 4 * C \
+                and self.attn.qkv.bias is not None:
+            # narrow UpscalingHead layers: the whole block is one fp32 kernel (csrc/small_block.cu)
+            a = self.attn
+            params = [_f32(t) for t in (self.norm1.weight, self.norm1.bias, a.qkv.weight, a.qkv.bias,
+                                        a.relative_position_bias_table, a.proj.weight, a.proj.bias, self.norm2.weight,
+                                        self.norm2.bias, self.mlp[0].weight, self.mlp[0].bias, self.mlp[3].weight,
+                                        self.mlp[3].bias)]
+            ops.swin_block_small(x, out, B, H, W, C, self.num_heads, self.shift_size, self.norm1.eps, params)
+            return out
         pk = self._packed()
         M = B * L
         qkv = torch.empty(M, 3 * C, device=x.device, dtype=torch.bfloat16)
@@ -201,7 +211,7 @@ class PatchMerging(nn.Module):
         Ho, Wo = (H + 1) // 2, (W + 1) // 2
 
         def build():
-            nv = packing.choose_chunk(2 * C, 128 if 4 * C > 384 else 256)
+            nv = packing.choose_chunk(2 * C, 64 if 4 * C > 384 else 256)   # K=768: the A tile alone is 192 KB
             return packing.pack_rowgemm(self.reduction.weight, None, nv) + (nv, _f32(self.norm.weight), _f32(self.norm.bias))
         Wp, _, NT, nch, nv, nw, nb = self._cache.get([self.reduction.weight, self.norm.weight, self.norm.bias], build)
         out = torch.empty(B, Ho * Wo, 2 * C, device=x.device, dtype=torch.float32)

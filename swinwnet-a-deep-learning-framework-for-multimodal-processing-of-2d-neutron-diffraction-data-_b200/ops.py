@@ -11,7 +11,7 @@ A_F32_LN, A_F32, A_BF16, A_MERGE_LN = 0, 1, 2, 3
 E_BF16, E_F32, E_EXPAND = 0, 1, 2
 
 LAUNCH_COUNT = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
-_LAUNCHES_PER_CALL = {"rowgemm": 1, "mlp": 1, "window_attention": 1, "cross_attention": 1, "patch_embed": 1,
+_LAUNCHES_PER_CALL = {"swin_block_small": 1, "rowgemm": 1,"mlp": 1, "window_attention": 1, "cross_attention": 1, "patch_embed": 1,
                       "seg_head": 2, "recon_head": 1, "copy_cols": 1, "sigmoid_mask": 1, "sigmoid_mask_mm": 2,
                       "normalize": 1}
 
@@ -64,6 +64,15 @@ def mlp(x, out, M, C, ln_w, ln_b, Wp, b1, b2p, eps=1e-5):
     _lib.check(_lib.load().swn_mlp(_ptr(x), _ptr(out), M, C, _ptr(ln_w), _ptr(ln_b), eps, _ptr(Wp), _ptr(b1), _ptr(b2p),
                                    _stream()), "swn_mlp")
     _count("mlp")
+
+
+def swin_block_small(x, out, B, H, W, C, nH, shift, eps, params):
+    """whole Swin block for C in {12, 24}; params = 13 fp32 device tensors (see include/swinwnet_b200.h)."""
+    _need_cuda(x, out, *params)
+    arr = (ctypes.c_void_p * 13)(*[p.data_ptr() for p in params])
+    _lib.check(_lib.load().swn_swin_block_small(_ptr(x), _ptr(out), B, H, W, C, nH, shift, eps, arr, _stream()),
+               "swn_swin_block_small")
+    _count("swin_block_small")
 
 
 def window_attention(qkv, out, qkv_bias, table, B, H, W, C, nH, shift=0):

@@ -244,6 +244,30 @@ def test_recon_head_and_glue():
     assert relerr(den, O.denormalize_piecewise(ref_norm, params)) <= 1e-5
 
 
+@pytest.mark.parametrize("C,H,W,shift", [(12, 10, 15, 0), (24, 7, 11, 0), (12, 13, 9, 0), (24, 10, 10, 2), (12, 5, 5, 3)])
+def test_swin_block_small_fused(C, H, W, shift):
+    """whole-block fp32 kernel for the UpscalingHead widths against the oracle block (incl. padding and shift)."""
+    B, nH = 2, 3
+    x = rnd(B, H * W, C, seed=1)
+    shapes = {"norm1.weight": (C,), "norm1.bias": (C,), "attn.qkv.weight": (3 * C, C), "attn.qkv.bias": (3 * C,),
+              "attn.relative_position_bias_table": (81, nH), "attn.proj.weight": (C, C), "attn.proj.bias": (C,),
+              "norm2.weight": (C,), "norm2.bias": (C,), "mlp.0.weight": (4 * C, C), "mlp.0.bias": (4 * C,),
+              "mlp.3.weight": (C, 4 * C), "mlp.3.bias": (C,)}
+    sd = {k: rnd(*s, seed=10 + i) * (0.3 if "weight" in k and len(s) == 2 else 0.2) for i, (k, s) in enumerate(shapes.items())}
+    sd["norm1.weight"] += 1.0
+    sd["norm2.weight"] += 1.0
+    ref = O.swin_block(sd, "", x, (H, W), nH, shift)
+    params = [sd[k].to(DEV).contiguous() for k in shapes]
+    xd = x.to(DEV)
+    out = torch.empty_like(xd)
+    ops.swin_block_small(xd, out, B, H, W, C, nH, shift, 1e-5, params)
+    torch.cuda.synchronize()
+    assert relerr(out, ref) <= 2e-5
+    ops.swin_block_small(xd, xd, B, H, W, C, nH, shift, 1e-5, params)   # in place
+    torch.cuda.synchronize()
+    assert relerr(xd, ref) <= 2e-5
+
+
 def test_copy_cols():
     src = rnd(37, 48, seed=1).to(DEV)
     dst = torch.zeros(37, 96, device=DEV)

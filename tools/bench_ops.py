@@ -56,6 +56,12 @@ for (L, C, nH, H, W) in SHAPES:
     M = B * L
     x = torch.randn(M, C, device=DEV)
     lw, lb = torch.ones(C, device=DEV), torch.zeros(C, device=DEV)
+    if "blk" in a.ops and C in (12, 24):
+        shp = [(C,), (C,), (3 * C, C), (3 * C,), (81, nH), (C, C), (C,), (C,), (C,), (4 * C, C), (4 * C,), (C, 4 * C), (C,)]
+        params = [torch.randn(*s, device=DEV) * 0.1 for s in shp]
+        out = torch.empty_like(x)
+        ms = timeit(lambda: ops.swin_block_small(x, out, B, H, W, C, nH, 0, 1e-5, params))
+        report("blk", M, C, ms, M * C * 8, (24.0 * C * C + 100.0 * C) * M)
     if "mlp" in a.ops:
         W1, b1 = torch.randn(4 * C, C, device=DEV) * C ** -0.5, torch.zeros(4 * C, device=DEV)
         W2, b2 = torch.randn(C, 4 * C, device=DEV) * (4 * C) ** -0.5, torch.zeros(C, device=DEV)
