@@ -49,6 +49,27 @@ def mlp_flops_per_diffraction():
     return 3 * per_pass + sr_head
 
 
+def shard_bounds(n_items, rank, world):
+    """contiguous shard [lo, hi) of `n_items` independent diffractions owned by `rank` (inference shards by batch;
+    no data-path collective)."""
+    base, rem = divmod(n_items, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def max_over_ranks(value, dist=None, device="cpu"):
+    """the job's time is the slowest rank's time: all-reduce MAX (NCCL on the GPU box, gloo in the CPU tests)."""
+    t = torch.tensor([float(value)], device=device)
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.item()
+
+
+def whole_job_rate(units_per_rank, world, steps, ms):
+    """aggregate throughput over all ranks (weak scaling: every rank processes `units_per_rank` per step)."""
+    return world * units_per_rank * steps / (ms / 1e3)
+
+
 class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
@@ -135,12 +156,12 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     man = json.load(open(os.path.join(ROOT, "tests", "golden", "manifest.json")))
-    from oracle import swinwnet_oracle as O        # weights/input generator + cpu_baseline leg only
+    import benchdata                               # seeded synthetic inputs / weights (no model math)
     model = S.SwinWNet(error_matrix=True, depths=DEPTHS)
-    model.load_state_dict(O.make_state_dict(man["wnet_em"], seed=1), strict=True)
+    model.load_state_dict(benchdata.make_state_dict(man["wnet_em"], seed=1), strict=True)
     inf = S.SwinWNetInference(model, dev, max_batch=64)
     B = args.batch
-    base = O.synthetic_diffractions(min(B, 8), seed=100 + rank, two_channel=False)
+    base = benchdata.synthetic_diffractions(min(B, 8), seed=100 + rank, two_channel=False)
     x_host = base.repeat((B + base.shape[0] - 1) // base.shape[0], 1, 1, 1)[:B].contiguous()
     x_host = (x_host * (1.0 + 0.01 * torch.arange(B).view(B, 1, 1, 1))).pin_memory()
     x_dev = x_host.to(dev)
@@ -172,10 +193,7 @@ def main():
             fn()
         e1.record()
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if dist is not None:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item()
+        return max_over_ranks(e0.elapsed_time(e1), dist, dev)
 
     def step_dev():
         inf(x_dev)
@@ -203,8 +221,8 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=3)
 
-    value = world * B * args.steps / (ms / 1e3)
-    e2e_v = world * B * args.steps / (ms_e2e / 1e3)
+    value = whole_job_rate(B, world, args.steps, ms)
+    e2e_v = whole_job_rate(B, world, args.steps, ms_e2e)
     pk = peaks()
     mlp_tflops = mlp_flops_per_diffraction() * B / (mlp_ms / 1e3) / 1e12
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W_,
@@ -225,7 +243,8 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count()
         torch.set_num_threads(cores)
-        sd = O.make_state_dict(man["wnet_em"], seed=1)
+        from oracle import swinwnet_oracle as O    # the checker, executed only for the reported CPU baseline
+        sd = benchdata.make_state_dict(man["wnet_em"], seed=1)
         xs = x_host[:1].clone()
         with torch.no_grad():
             O.st_pipeline(sd, xs)

@@ -49,7 +49,6 @@ def test_case_A_pipeline_vs_reference_golden(wnet_em, golden):
     assert out is inf.images_masked_hr
     # PSNR gate (tests.py:349-357 protocol: clamp(0,1), data_range 1) against the normalised HR reference output
     t = golden["A_upscaled_norm"]
-    assert abs(psnr(inf.upscaled_norm.cpu(), t) - psnr(t, t)) >= 0  # defined
     assert psnr(inf.upscaled_norm.cpu(), t) > 40.0
 
 
@@ -148,3 +147,63 @@ def test_state_dict_round_trip_and_repack(manifest):
     assert relerr(y2, O.swin_unet(sd2, x.cpu())) <= TOL
     for k, v in m.state_dict().items():
         assert torch.equal(v.cpu(), sd2[k]), k
+
+
+@pytest.fixture(scope="module")
+def surrogate(manifest):
+    """"trained-like" surrogate checkpoint (damped seeded body + fitted conv heads, oracle/make_surrogate_heads.py):
+    segmentation probabilities are decisive (1.7 % of pixels within 0.05 of the threshold) and the SR output has
+    diffraction peaks, so the mask / PSNR / physics gates are meaningful."""
+    import os
+    sd = O.surrogate_state_dict(manifest["wnet_em"], os.path.join(os.path.dirname(__file__), "golden", "surrogate_heads.pt"))
+    m = S.SwinWNet(error_matrix=True, depths=D2)
+    m.load_state_dict(sd, strict=True)
+    return sd, m.to(DEV).eval()
+
+
+def test_acceptance_gates_surrogate_checkpoint(surrogate):
+    """north_star gates on the reference's evaluation protocols, CUDA path vs fp32 oracle, same inputs and weights:
+    logits / images <= 2e-2 max-norm; binarised masks (>= 0.5, tests.py:12-16) identical on >= 99.9 % of pixels;
+    PSNR (clamp(0,1), data_range 1, tests.py:332-357) within 0.05 dB; d-space integral- and peak-intensity distortion
+    (tests.py:401-447 call pattern) within 1 % (batch mean)."""
+    import numpy as np
+    from oracle import diffraction_metrics_oracle as DM
+    F = torch.nn.functional
+    sd, model = surrogate
+    B = 4
+    images = O.synthetic_diffractions(B, seed=41)                     # [B,2,250,480]
+
+    def protocol(seg1, upscale, seg2, dev):
+        x = images.to(dev)
+        seg, skips = seg1(x)
+        xm = x * torch.sigmoid(seg)
+        lr = F.interpolate(xm, scale_factor=0.5, mode="bilinear", align_corners=False)
+        norm_lr, _ = O.normalize_piecewise(lr)
+        norm_hr, params = O.normalize_piecewise(xm)
+        sr, _ = upscale(norm_lr, skips)                               # physics / PSNR protocol: half-resolution input
+        den = O.denormalize_piecewise(sr, params)
+        up, skips_sr = upscale(norm_hr, skips)                        # inference pipeline: full resolution
+        seg_hr, _ = seg2(O.denormalize_piecewise(up, params), skips_sr)
+        return [t.float().cpu() for t in (seg, lr, sr, den, norm_hr, up, seg_hr)]
+
+    with torch.no_grad():
+        c = protocol(model.segment_1, model.upscale, model.segment_2, DEV)
+        o = protocol(lambda x: O.segment_1(sd, x), lambda x, s: O.upscale(sd, x, s), lambda x, s: O.segment_2(sd, x, s), "cpu")
+    names = ("seg_lr", "lr", "sr_half", "den", "norm_hr", "up_full", "seg_hr")
+    for n, a, b in zip(names, c, o):
+        e = relerr(a, b)
+        print(f"max-norm rel err {n}: {e:.3e}")
+        assert e <= TOL, n
+    for n, a, b in (("LR", c[0], o[0]), ("HR", c[6], o[6])):
+        agree = ((torch.sigmoid(a) >= 0.5) == (torch.sigmoid(b) >= 0.5)).float().mean().item()
+        print(f"mask agreement {n}: {agree:.6f}  (foreground fraction {(torch.sigmoid(b) >= 0.5).float().mean().item():.3f})")
+        assert agree >= 0.999, (n, agree)
+    p_c, p_o = psnr(c[2], o[4]), psnr(o[2], o[4])
+    print("PSNR cuda / oracle:", p_c, p_o)
+    assert abs(p_c - p_o) <= 0.05
+    m_c = DM.physical_metrics(c[3].numpy(), o[1].numpy())
+    m_o = DM.physical_metrics(o[3].numpy(), o[1].numpy())
+    for k in ("Integral Intensity", "Peak Intensity"):
+        a, b = float(np.mean(m_c[k])), float(np.mean(m_o[k]))
+        print(k, "cuda / oracle:", a, b, "per-sample", m_c[k], m_o[k])
+        assert b > 0 and abs(a - b) <= 0.01 * abs(b), (k, a, b)

@@ -73,3 +73,24 @@ def test_shift_mask_is_standard_swin():
     rid = O.shift_region_ids(10, 10, 5, 2)
     assert rid.unique().numel() == 9
     assert rid[0, 0] == 0 and rid[9, 9] == 8 and rid[5, 9] == 5
+
+
+def test_physics_metric_oracle_vs_reference_golden():
+    """oracle/diffraction_metrics_oracle.py against outputs of the unmodified reference Diffraction_metrics.py
+    (tests/golden/physics_metrics.json, made by oracle/make_golden_physics.py)."""
+    import json
+    import os
+    import numpy as np
+    from oracle import diffraction_metrics_oracle as DM
+    from oracle.make_golden_physics import inputs
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "physics_metrics.json")))
+    for seed, g in gold.items():
+        pred, true = inputs(int(seed))
+        m = DM.physical_metrics(pred.numpy(), true.numpy())
+        for k in ("Integral Intensity", "Peak Intensity", "Shape"):
+            assert np.allclose(m[k], g["metrics"][k], rtol=2e-4, atol=1e-6), (seed, k, m[k], g["metrics"][k])
+            assert sum(g["metrics"][k]) > 0          # the fixture exercises matched peaks
+        for b in range(pred.shape[0]):
+            _, I = DM.to_d_space(pred[b, 0].numpy(), DM.D_CENTERS_HR)
+            assert abs(float(I.sum()) - g["I_sum"][b]) <= 1e-5 * g["I_sum"][b]
+            assert int(I.argmax()) == g["I_argmax"][b]

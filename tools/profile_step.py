@@ -9,7 +9,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import swinwnet_b200 as S  # noqa: E402
-from oracle import swinwnet_oracle as O  # noqa: E402  (weight / input generator only)
+import benchdata as O  # noqa: E402  (seeded weight / input generator, no model math)
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=64)
