@@ -227,7 +227,7 @@ def main():
     mlp_tflops = mlp_flops_per_diffraction() * B / (mlp_ms / 1e3) / 1e12
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W_,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
+            "dtype": "bf16" if ops.operand_dtype() == torch.bfloat16 else "fp16", "data": "synthetic",
             "config": {"workload": "SwinWNet multimodal ST pipeline [B,2,250,480] (configs[1]), depths [2,2,2,2], "
                                    "random-init weights", "batch_per_gpu": B, "global_batch": B * world,
                        "l2_policy": "per-step working set (>2 GB of activations) exceeds the 126 MB L2"},

@@ -47,6 +47,7 @@ typedef struct swn_rowgemm_args {
 const char* swn_last_error(void);
 int swn_abi_version(void);
 int swn_sizeof_rowgemm_args(void); /* lets FFI bindings verify their struct mirror */
+int swn_operand_is_bf16(void);     /* 16-bit tensor-core operand type of this build: 0 = IEEE fp16 (default), 1 = bf16 */
 
 /* Tile configuration of the fused MLP for channel width C (the weight packer must use the same):
  * HC = hidden-chunk width, TR = fc2 output rows per weight tile. */

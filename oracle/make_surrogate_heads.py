@@ -106,6 +106,28 @@ def main():
         return F.mse_loss(out[:, :, :norm_hr.shape[2], :norm_hr.shape[3]], norm_hr) * 100.0
     fit(list(rec_p.values()), rec_loss, 300, 3e-3)
     sd.update({k: v.detach() for k, v in rec_p.items()})
+    # ---- stage 3: refit the (shared) segmentation head on LR + HR features, as FullModelTrainer's odd steps do ----
+    print("refitting segmentator_head on LR + HR features")
+    with torch.no_grad():
+        norm_hr2, params = O.normalize_piecewise(xm)
+        up, skips_sr = O.upscale(sd, norm_hr2, skips)
+        den = O.denormalize_piecewise(up, params)
+        t, pres2 = O.patch_embed(sd, "patch_embed.", den, 2)
+        res2 = (pres2[0] // 4, pres2[1] // 4)
+        sk2, rl2, bres2 = O.encoder(sd, "segmentator_encoder.", t, res2, O.DEPTHS, O.HEADS)
+        sk2[-2], sk2[-1] = O.multi_scale_cross_attention(sd, "ca_sr_to_seg.", [sk2[-2], sk2[-1]], [skips_sr[-2], skips_sr[-1]])
+        xb2 = O.bottleneck(sd, "segmentator_bottleneck.", sk2[-1], bres2, O.HEADS[-1])
+        xd_hr, _ = O.decoder(sd, "segmentator_decoder.", xb2, bres2, sk2, rl2, O.DEPTHS, O.HEADS)
+        target_hr = peak_mask(F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False))
+    seg_p = {k: sd[k].clone().requires_grad_(True) for k in SEG_KEYS}
+
+    def seg_loss2():
+        w = {**sd, **seg_p}
+        lo = O.segmentation_head(w, "segmentator_head.", xd, pres, 1)
+        hi = O.segmentation_head(w, "segmentator_head.", xd_hr, pres2, 2)
+        return F.binary_cross_entropy_with_logits(lo, target) + F.binary_cross_entropy_with_logits(hi, target_hr)
+    fit(list(seg_p.values()), seg_loss2, 200, 3e-3)
+    sd.update({k: v.detach() for k, v in seg_p.items()})
     out = {k: sd[k].clone() for k in SEG_KEYS + REC_KEYS}
     torch.save(out, os.path.join(ROOT, "tests", "golden", "surrogate_heads.pt"))
     print("saved", sum(v.numel() for v in out.values()), "parameters")

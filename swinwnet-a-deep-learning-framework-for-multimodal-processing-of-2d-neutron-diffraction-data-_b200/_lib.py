@@ -28,6 +28,7 @@ SIGNATURES = {
     "swn_last_error": (ctypes.c_char_p, []),
     "swn_abi_version": (c_int, []),
     "swn_sizeof_rowgemm_args": (c_int, []),
+    "swn_operand_is_bf16": (c_int, []),
     "swn_mlp_config": (c_int, [c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
     "swn_rowgemm": (c_int, [ctypes.POINTER(RowGemmArgs), c_void_p]),
     "swn_mlp": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p,

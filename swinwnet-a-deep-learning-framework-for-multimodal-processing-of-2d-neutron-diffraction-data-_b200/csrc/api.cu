@@ -41,6 +41,7 @@ extern "C" {
 const char* swn_last_error(void) { return g_err; }
 int swn_abi_version(void) { return SWN_ABI_VERSION; }
 int swn_sizeof_rowgemm_args(void) { return (int)sizeof(swn_rowgemm_args); }
+int swn_operand_is_bf16(void) { return SWN_OPERAND_BF16; }
 
 int swn_mlp_config(int C, int* HC, int* TR) {
   SWN_CHECK(C >= 4 && C % 4 == 0 && C <= 384 && HC && TR, "mlp_config: unsupported C=%d", C);
@@ -54,7 +55,7 @@ int swn_rowgemm(const swn_rowgemm_args* a, void* stream) {
   p.A = a->A; p.a_mode = a->a_mode; p.M = a->M; p.K = a->K; p.lda = a->lda;
   p.ln_w = a->ln_w; p.ln_b = a->ln_b; p.ln_eps = a->ln_eps;
   p.gH = a->gH; p.gW = a->gW; p.gC = a->gC; p.gHo = a->gHo; p.gWo = a->gWo;
-  p.Wp = reinterpret_cast<const __nv_bfloat16*>(a->Wp);
+  p.Wp = reinterpret_cast<const op_t*>(a->Wp);
   p.NT = a->NT; p.nchunks = a->nchunks; p.n_valid = a->n_valid;
   p.e_mode = a->e_mode; p.bias = a->bias; p.out = a->out; p.ldo = a->ldo;
   p.res = a->res; p.ldres = a->ldres; p.alpha = a->alpha;
@@ -77,7 +78,7 @@ int swn_mlp(const float* x, float* out, int M, int C, const float* ln_w, const f
   SWN_CHECK(C >= 4 && C % 4 == 0 && C <= 384, "mlp: unsupported C=%d", C);
   MlpParams p{};
   p.x = x; p.out = out; p.M = M; p.C = C; p.ln_w = ln_w; p.ln_b = ln_b; p.ln_eps = ln_eps;
-  p.Wp = reinterpret_cast<const __nv_bfloat16*>(Wp); p.b1 = b1; p.b2 = b2;
+  p.Wp = reinterpret_cast<const op_t*>(Wp); p.b1 = b1; p.b2 = b2;
   mlp_config(C, &p.HC, &p.TR);
   if (C <= 96) return launch_mlp_persist(p, num_sms(), reinterpret_cast<cudaStream_t>(stream));
   return launch_mlp(p, reinterpret_cast<cudaStream_t>(stream));
@@ -96,7 +97,7 @@ int swn_window_attention(const void* qkv, void* out, const float* qkv_bias, cons
                          int C, int num_heads, int shift, void* stream) {
   SWN_CHECK(qkv && out && qkv_bias && rpb_table, "window_attention: null pointer");
   SWN_CHECK(B > 0 && H > 0 && W > 0 && C % 4 == 0 && num_heads > 0 && shift >= 0, "window_attention: bad sizes");
-  WinAttnParams p{reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), qkv_bias, rpb_table,
+  WinAttnParams p{reinterpret_cast<const op_t*>(qkv), reinterpret_cast<op_t*>(out), qkv_bias, rpb_table,
                   B, H, W, C, num_heads, shift};
   return launch_window_attn(p, reinterpret_cast<cudaStream_t>(stream));
 }
@@ -104,8 +105,8 @@ int swn_window_attention(const void* qkv, void* out, const float* qkv_bias, cons
 int swn_cross_attention(const void* q, const void* kv, void* out, int B, int Lq, int Lk, int C, int num_heads,
                         void* stream) {
   SWN_CHECK(q && kv && out, "cross_attention: null pointer");
-  CrossAttnParams p{reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(kv),
-                    reinterpret_cast<__nv_bfloat16*>(out), B, Lq, Lk, C, num_heads};
+  CrossAttnParams p{reinterpret_cast<const op_t*>(q), reinterpret_cast<const op_t*>(kv),
+                    reinterpret_cast<op_t*>(out), B, Lq, Lk, C, num_heads};
   return launch_cross_attn(p, reinterpret_cast<cudaStream_t>(stream));
 }
 

@@ -14,7 +14,7 @@ constexpr int CA_BQ = 64, CA_BK = 64;
 
 __device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
   asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      "mma.sync.aligned.m16n8k16.row.col.f32." SWN_MMA_T "." SWN_MMA_T ".f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -26,16 +26,16 @@ template <int HD>
 __global__ void __launch_bounds__(CA_THREADS) cross_attn_kernel(const CrossAttnParams p) {
   constexpr int LDS = HD + 8;  // padded smem row (bf16 elements)
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  __nv_bfloat16* q_s = reinterpret_cast<__nv_bfloat16*>(smem_raw);
-  __nv_bfloat16* k_s = q_s + CA_BQ * LDS;
-  __nv_bfloat16* v_s = k_s + CA_BK * LDS;
+  op_t* q_s = reinterpret_cast<op_t*>(smem_raw);
+  op_t* k_s = q_s + CA_BQ * LDS;
+  op_t* v_s = k_s + CA_BK * LDS;
 
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * CA_BQ;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
   const int C = p.C;
-  const __nv_bfloat16* qg = p.q + ((long long)b * p.Lq) * C + h * HD;
-  const __nv_bfloat16* kg = p.kv + ((long long)b * p.Lk) * (2 * C) + h * HD;
-  const __nv_bfloat16* vg = kg + C;
+  const op_t* qg = p.q + ((long long)b * p.Lq) * C + h * HD;
+  const op_t* kg = p.kv + ((long long)b * p.Lk) * (2 * C) + h * HD;
+  const op_t* vg = kg + C;
 
   constexpr int VPR = HD / 8;  // 16-byte vectors per row
   for (int i = threadIdx.x; i < CA_BQ * VPR; i += CA_THREADS) {
@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(CA_THREADS) cross_attn_kernel(const CrossAttnP
   // Q fragments stay in registers for the whole KV sweep
   uint32_t qf[HD / 16][4];
   {
-    const __nv_bfloat16* qr = q_s + (warp * 16 + g) * LDS + t4 * 2;
+    const op_t* qr = q_s + (warp * 16 + g) * LDS + t4 * 2;
 #pragma unroll
     for (int ks = 0; ks < HD / 16; ++ks) {
       qf[ks][0] = *reinterpret_cast<const uint32_t*>(qr + ks * 16);
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(CA_THREADS) cross_attn_kernel(const CrossAttnP
 #pragma unroll
     for (int n = 0; n < CA_BK / 8; ++n) {
       s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
-      const __nv_bfloat16* kr = k_s + (n * 8 + g) * LDS + t4 * 2;
+      const op_t* kr = k_s + (n * 8 + g) * LDS + t4 * 2;
 #pragma unroll
       for (int ks = 0; ks < HD / 16; ++ks) {
         const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kr + ks * 16);
@@ -134,10 +134,10 @@ __global__ void __launch_bounds__(CA_THREADS) cross_attn_kernel(const CrossAttnP
 #pragma unroll
     for (int ks = 0; ks < CA_BK / 16; ++ks) {
       uint32_t pa[4];
-      pa[0] = pack_bf16(s[2 * ks][0], s[2 * ks][1]);
-      pa[1] = pack_bf16(s[2 * ks][2], s[2 * ks][3]);
-      pa[2] = pack_bf16(s[2 * ks + 1][0], s[2 * ks + 1][1]);
-      pa[3] = pack_bf16(s[2 * ks + 1][2], s[2 * ks + 1][3]);
+      pa[0] = pack_op(s[2 * ks][0], s[2 * ks][1]);
+      pa[1] = pack_op(s[2 * ks][2], s[2 * ks][3]);
+      pa[2] = pack_op(s[2 * ks + 1][0], s[2 * ks + 1][1]);
+      pa[3] = pack_op(s[2 * ks + 1][2], s[2 * ks + 1][3]);
       const uint32_t vrow = smem_u32(v_s + (ks * 16 + (lane & 15)) * LDS);
 #pragma unroll
       for (int n = 0; n < HD / 8; ++n) {
@@ -155,11 +155,11 @@ __global__ void __launch_bounds__(CA_THREADS) cross_attn_kernel(const CrossAttnP
   }
   const float inv0 = 1.0f / l_run[0], inv1 = 1.0f / l_run[1];
   const int qa = q0 + warp * 16 + g, qb = qa + 8;
-  __nv_bfloat16* og = p.out + ((long long)b * p.Lq) * C + h * HD + t4 * 2;
+  op_t* og = p.out + ((long long)b * p.Lq) * C + h * HD + t4 * 2;
 #pragma unroll
   for (int n = 0; n < HD / 8; ++n) {
-    if (qa < p.Lq) *reinterpret_cast<uint32_t*>(og + (long long)qa * C + n * 8) = pack_bf16(o[n][0] * inv0, o[n][1] * inv0);
-    if (qb < p.Lq) *reinterpret_cast<uint32_t*>(og + (long long)qb * C + n * 8) = pack_bf16(o[n][2] * inv1, o[n][3] * inv1);
+    if (qa < p.Lq) *reinterpret_cast<uint32_t*>(og + (long long)qa * C + n * 8) = pack_op(o[n][0] * inv0, o[n][1] * inv0);
+    if (qb < p.Lq) *reinterpret_cast<uint32_t*>(og + (long long)qb * C + n * 8) = pack_op(o[n][2] * inv1, o[n][3] * inv1);
   }
 }
 

@@ -20,7 +20,7 @@ struct RowGemmParams {
   float ln_eps;
   int gH, gW, gC, gHo, gWo;  // A_MERGE_LN: source grid [B,gH,gW,gC] -> rows over [B,gHo,gWo]
   // B operand: packed [NT x 64] bf16 SWIZZLE_128B tiles, order (chunk, kblock)
-  const __nv_bfloat16* Wp;
+  const op_t* Wp;
   int NT, nchunks, n_valid;
   // epilogue
   int e_mode;
@@ -50,7 +50,7 @@ struct MlpParams {
   const float* ln_w;
   const float* ln_b;
   float ln_eps;
-  const __nv_bfloat16* Wp;  // packed fc1/fc2 tile stream (see pack_mlp_weights in packing.py)
+  const op_t* Wp;  // packed fc1/fc2 tile stream (see pack_mlp_weights in packing.py)
   const float* b1;          // [4C]
   const float* b2;          // [C16] (zero padded)
   int HC;                   // hidden chunk width
@@ -63,8 +63,8 @@ int launch_mlp_persist(MlpParams p, int num_sms, cudaStream_t stream);  // C <= 
 
 // ---- window_attn.cu -------------------------------------------------------------------------
 struct WinAttnParams {
-  const __nv_bfloat16* qkv;  // [B*H*W, 3C] token order
-  __nv_bfloat16* out;        // [B*H*W, C]
+  const op_t* qkv;  // [B*H*W, 3C] token order
+  op_t* out;        // [B*H*W, C]
   const float* qkv_bias;     // [3C]: q/k/v of zero-padded tokens (pad happens after norm1)
   const float* rpb_table;    // [81, nH]
   int B, H, W, C, nH, shift;
@@ -83,9 +83,9 @@ int launch_swin_block_small(SmallBlockParams p, int num_sms, cudaStream_t stream
 
 // ---- cross_attn.cu --------------------------------------------------------------------------
 struct CrossAttnParams {
-  const __nv_bfloat16* q;   // [B, Lq, C]
-  const __nv_bfloat16* kv;  // [B, Lk, 2C]  (k | v)
-  __nv_bfloat16* out;       // [B, Lq, C]
+  const op_t* q;   // [B, Lq, C]
+  const op_t* kv;  // [B, Lk, 2C]  (k | v)
+  op_t* out;       // [B, Lq, C]
   int B, Lq, Lk, C, nH;
 };
 int launch_cross_attn(CrossAttnParams p, cudaStream_t stream);

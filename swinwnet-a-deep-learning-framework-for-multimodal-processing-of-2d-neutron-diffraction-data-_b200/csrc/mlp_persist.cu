@@ -16,10 +16,11 @@
 
 namespace swn {
 
-constexpr int MP_WARPS = 16;
+constexpr int MP_EPI_SPLIT = 2;                 // epilogue warps per TMEM lane group (they split the columns)
+constexpr int MP_WARPS = 8 + 4 * MP_EPI_SPLIT;
 constexpr int MP_THREADS = MP_WARPS * 32;
 constexpr int MP_LN_WARPS = 4;
-constexpr int MP_EPI_THREADS = 256;
+constexpr int MP_EPI_THREADS = 128 * MP_EPI_SPLIT;
 
 struct MpSmem {
   uint64_t full[8], empty[8];
@@ -244,8 +245,8 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
               y[hh * 4 + 0] = y[hh * 4 + 1] = y[hh * 4 + 2] = y[hh * 4 + 3] = 0.f;
             }
           }
-          pk[0] = pack_bf16(y[0], y[1]); pk[1] = pack_bf16(y[2], y[3]);
-          pk[2] = pack_bf16(y[4], y[5]); pk[3] = pack_bf16(y[6], y[7]);
+          pk[0] = pack_op(y[0], y[1]); pk[1] = pack_op(y[2], y[3]);
+          pk[2] = pack_op(y[4], y[5]); pk[3] = pack_op(y[6], y[7]);
         }
         *reinterpret_cast<uint4*>(a_smem + (k >> 6) * A_KBLOCK_BYTES + sw128_offset(row, k & 63)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
@@ -253,14 +254,24 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
       mbar_arrive(&sh->a_full);
     }
   } else if (warp >= 8) {
-    // ===== epilogue warps 8..15 =====
+    // ===== epilogue warps 8..: MP_EPI_SPLIT warps per TMEM lane group split the 16-column blocks =====
     const int lg = warp & 3;
-    const int half = (warp - 8) >> 2;
+    const int part = (warp - 8) >> 2;
     const int r = lg * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
-    const int cb_beg = (steps2 & 1) ? (half ? steps2 : 0) : half * (steps2 >> 1);
-    const int cb_end = (steps2 & 1) ? steps2 : cb_beg + (steps2 >> 1);
-    float v[32];
+    int cb_beg = 0, cb_end = 0;   // 16-column blocks of a hidden chunk owned by this warp
+    if (steps2 % MP_EPI_SPLIT == 0) {
+      cb_beg = part * (steps2 / MP_EPI_SPLIT);
+      cb_end = cb_beg + steps2 / MP_EPI_SPLIT;
+    } else if (steps2 % 2 == 0) {
+      if (part < 2) {
+        cb_beg = part * (steps2 / 2);
+        cb_end = cb_beg + steps2 / 2;
+      }
+    } else if (part == 0) {
+      cb_end = steps2;
+    }
+    float v[16];
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int s = it & 1;
@@ -275,26 +286,20 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
         uint8_t* hrow = hs_smem + buf * nkk * A_KBLOCK_BYTES;
         const float* bj = b1s + j * HC;
         const uint32_t t_chunk = lane_addr + (uint32_t)(hbase + buf * HC);
-        for (int cb = cb_beg; cb < cb_end; cb += 2) {
-          const bool two = cb + 1 < cb_end;
+        for (int cb = cb_beg; cb < cb_end; ++cb) {
           tmem_ld16(t_chunk + cb * 16, v);
-          if (two) tmem_ld16(t_chunk + cb * 16 + 16, v + 16);
           tmem_ld_wait();
+          const int k = cb * 16;
+          uint32_t pk[8];
 #pragma unroll
-          for (int hb = 0; hb < 2; ++hb) {
-            if (hb == 1 && !two) break;
-            const int k = (cb + hb) * 16;
-            uint32_t pk[8];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 bb = *reinterpret_cast<const float4*>(bj + k + 4 * i);
-              pk[2 * i] = pack_bf16(gelu_erf(v[hb * 16 + 4 * i] + bb.x), gelu_erf(v[hb * 16 + 4 * i + 1] + bb.y));
-              pk[2 * i + 1] = pack_bf16(gelu_erf(v[hb * 16 + 4 * i + 2] + bb.z), gelu_erf(v[hb * 16 + 4 * i + 3] + bb.w));
-            }
-            uint8_t* kb_base = hrow + (k >> 6) * A_KBLOCK_BYTES;
-            *reinterpret_cast<uint4*>(kb_base + sw128_offset(r, k & 63)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            *reinterpret_cast<uint4*>(kb_base + sw128_offset(r, (k & 63) + 8)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          for (int i = 0; i < 4; ++i) {
+            const float4 bb = *reinterpret_cast<const float4*>(bj + k + 4 * i);
+            pk[2 * i] = pack_op(gelu_erf(v[4 * i] + bb.x), gelu_erf(v[4 * i + 1] + bb.y));
+            pk[2 * i + 1] = pack_op(gelu_erf(v[4 * i + 2] + bb.z), gelu_erf(v[4 * i + 3] + bb.w));
           }
+          uint8_t* kb_base = hrow + (k >> 6) * A_KBLOCK_BYTES;
+          *reinterpret_cast<uint4*>(kb_base + sw128_offset(r, k & 63)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(kb_base + sw128_offset(r, (k & 63) + 8)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         }
         tc_fence_before();
         fence_proxy_async();
@@ -305,7 +310,7 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
       mbar_wait(&sh->y_full, (uint32_t)it & 1u);
       tc_fence_after();
       const uint8_t* res = stg + s * TILE_M * rs + r * rs;
-      for (int cb = half; cb < (C16 >> 4); cb += 2) {
+      for (int cb = part; cb < (C16 >> 4); cb += MP_EPI_SPLIT) {
         tmem_ld16(lane_addr + (uint32_t)(cb * 16), v);
         tmem_ld_wait();
         if (row_ok) {

@@ -83,13 +83,13 @@ __global__ void __launch_bounds__(RG_THREADS, 1) rowgemm_kernel(const RowGemmPar
     constexpr int UNR = KV == 1 ? 4 : (KV <= 3 ? 2 : 1);
     const int M = p.M;
     if (p.a_mode == A_BF16) {
-      const __nv_bfloat16* A = reinterpret_cast<const __nv_bfloat16*>(p.A);
+      const op_t* A = reinterpret_cast<const op_t*>(p.A);
       const int lda = p.lda;
       build_a_tile<LPR, KV, UNR, false>(a_smem, p.K, K16, nullptr, nullptr, 0.f, warp, RG_WARPS, lane, [&](int r, int k) {
         const long long m = m0 + r;
         if (m >= M) return make_float4(0.f, 0.f, 0.f, 0.f);
         const uint2 raw = *reinterpret_cast<const uint2*>(A + m * lda + k);
-        return make_float4(bf16_lo(raw.x), bf16_hi(raw.x), bf16_lo(raw.y), bf16_hi(raw.y));
+        return make_float4(op_lo(raw.x), op_hi(raw.x), op_lo(raw.y), op_hi(raw.y));
       });
     } else if (p.a_mode == A_MERGE_LN) {
       const float* A = reinterpret_cast<const float*>(p.A);
@@ -255,17 +255,17 @@ __global__ void __launch_bounds__(RG_THREADS, 1) rowgemm_kernel(const RowGemmPar
             }
           }
           if (p.e_mode == E_BF16) {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.ldo + col0 + c0;
+            op_t* o = reinterpret_cast<op_t*>(p.out) + m * p.ldo + col0 + c0;
             if (vec8 && c0 + 16 <= p.n_valid) {
-              *reinterpret_cast<uint4*>(o) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
-                                                        pack_bf16(v[6], v[7]));
-              *reinterpret_cast<uint4*>(o + 8) = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]),
-                                                            pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+              *reinterpret_cast<uint4*>(o) = make_uint4(pack_op(v[0], v[1]), pack_op(v[2], v[3]), pack_op(v[4], v[5]),
+                                                        pack_op(v[6], v[7]));
+              *reinterpret_cast<uint4*>(o + 8) = make_uint4(pack_op(v[8], v[9]), pack_op(v[10], v[11]),
+                                                            pack_op(v[12], v[13]), pack_op(v[14], v[15]));
             } else {
 #pragma unroll
               for (int j4 = 0; j4 < 16; j4 += 4)
                 if (c0 + j4 < p.n_valid)
-                  *reinterpret_cast<uint2*>(o + j4) = make_uint2(pack_bf16(v[j4], v[j4 + 1]), pack_bf16(v[j4 + 2], v[j4 + 3]));
+                  *reinterpret_cast<uint2*>(o + j4) = make_uint2(pack_op(v[j4], v[j4 + 1]), pack_op(v[j4 + 2], v[j4 + 3]));
             }
           } else {
             float* o = reinterpret_cast<float*>(p.out) + m * p.ldo + col0 + c0;

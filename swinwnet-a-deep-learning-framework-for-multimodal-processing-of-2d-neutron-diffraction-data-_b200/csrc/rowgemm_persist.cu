@@ -207,8 +207,8 @@ __global__ void __launch_bounds__(RP_THREADS, 1) rowgemm_persist_kernel(const Ro
                 y[hh * 4 + 0] = y[hh * 4 + 1] = y[hh * 4 + 2] = y[hh * 4 + 3] = 0.f;
               }
             }
-            pk[0] = pack_bf16(y[0], y[1]); pk[1] = pack_bf16(y[2], y[3]);
-            pk[2] = pack_bf16(y[4], y[5]); pk[3] = pack_bf16(y[6], y[7]);
+            pk[0] = pack_op(y[0], y[1]); pk[1] = pack_op(y[2], y[3]);
+            pk[2] = pack_op(y[4], y[5]); pk[3] = pack_op(y[6], y[7]);
           }
         }
         *reinterpret_cast<uint4*>(a_smem + (k >> 6) * A_KBLOCK_BYTES + sw128_offset(row, k & 63)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -254,16 +254,16 @@ __global__ void __launch_bounds__(RP_THREADS, 1) rowgemm_persist_kernel(const Ro
             v[j4] += bv.x; v[j4 + 1] += bv.y; v[j4 + 2] += bv.z; v[j4 + 3] += bv.w;
           }
           if (EM == E_BF16) {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + m * ldo + col0 + c0;
+            op_t* o = reinterpret_cast<op_t*>(p.out) + m * ldo + col0 + c0;
             if (vec8 && nvb == 16) {
-              *reinterpret_cast<uint4*>(o) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
-                                                        pack_bf16(v[6], v[7]));
-              *reinterpret_cast<uint4*>(o + 8) = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]),
-                                                            pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+              *reinterpret_cast<uint4*>(o) = make_uint4(pack_op(v[0], v[1]), pack_op(v[2], v[3]), pack_op(v[4], v[5]),
+                                                        pack_op(v[6], v[7]));
+              *reinterpret_cast<uint4*>(o + 8) = make_uint4(pack_op(v[8], v[9]), pack_op(v[10], v[11]),
+                                                            pack_op(v[12], v[13]), pack_op(v[14], v[15]));
             } else {
 #pragma unroll
               for (int j4 = 0; j4 < 16; j4 += 4)
-                if (j4 < nvb) *reinterpret_cast<uint2*>(o + j4) = make_uint2(pack_bf16(v[j4], v[j4 + 1]), pack_bf16(v[j4 + 2], v[j4 + 3]));
+                if (j4 < nvb) *reinterpret_cast<uint2*>(o + j4) = make_uint2(pack_op(v[j4], v[j4 + 1]), pack_op(v[j4 + 2], v[j4 + 3]));
             }
           } else {
             float* o = reinterpret_cast<float*>(p.out) + m * ldo + col0 + c0;

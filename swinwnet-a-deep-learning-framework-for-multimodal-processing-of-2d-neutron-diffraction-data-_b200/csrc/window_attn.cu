@@ -24,7 +24,7 @@ constexpr int WS = 5, WN = 25, WR = 32;  // window side, tokens per window, padd
 
 __device__ __forceinline__ void wa_mma(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
   asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      "mma.sync.aligned.m16n8k16.row.col.f32." SWN_MMA_T "." SWN_MMA_T ".f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(WA_THREADS) window_attn_kernel(const WinAttnPa
   constexpr int NTO = HD >= 8 ? HD / 8 : 1;    // 8-wide output column tiles of O = P V
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int C = p.C, nH = p.nH;
-  __nv_bfloat16* qkv_s = reinterpret_cast<__nv_bfloat16*>(smem_raw);                       // [wpb][32][RS]
+  op_t* qkv_s = reinterpret_cast<op_t*>(smem_raw);                       // [wpb][32][RS]
   float* tab_s = reinterpret_cast<float*>(smem_raw + (size_t)wpb * WR * RS * 2);          // [81*nH]
   long long* tok_s = reinterpret_cast<long long*>(tab_s + ((81 * nH + 1) & ~1));         // [wpb][32]
   int* rid_s = reinterpret_cast<int*>(tok_s + wpb * WR);                                  // [wpb][32]
@@ -81,9 +81,9 @@ __global__ void __launch_bounds__(WA_THREADS) window_attn_kernel(const WinAttnPa
   const bool vec8 = (3 * C) % 8 == 0;  // 16-byte vectors when the row length allows
   for (int slot = warp; slot < wpb * WR; slot += WA_THREADS / 32) {
     const long long tok = tok_s[slot];
-    __nv_bfloat16* dst = qkv_s + (size_t)slot * RS;
+    op_t* dst = qkv_s + (size_t)slot * RS;
     if (tok >= 0) {
-      const __nv_bfloat16* src = p.qkv + tok * (3 * C);
+      const op_t* src = p.qkv + tok * (3 * C);
       // cp.async: every row of the CTA is in flight at once, so DRAM latency is paid once per CTA
       if (vec8) {
         for (int c = lane * 8; c < 3 * C; c += 256)
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(WA_THREADS) window_attn_kernel(const WinAttnPa
         uint2 val = make_uint2(0u, 0u);
         if (tok == -1) {
           const float4 bv = *reinterpret_cast<const float4*>(p.qkv_bias + c);
-          val = make_uint2(pack_bf16(bv.x, bv.y), pack_bf16(bv.z, bv.w));
+          val = make_uint2(pack_op(bv.x, bv.y), pack_op(bv.z, bv.w));
         }
         *reinterpret_cast<uint2*>(dst + c) = val;
       }
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(WA_THREADS) window_attn_kernel(const WinAttnPa
   for (int pr = warp; pr < wpb * nH; pr += WA_THREADS / 32) {
     const int wl = pr / nH, h = pr - wl * nH;
     if (w0 + wl >= n_windows) continue;
-    __nv_bfloat16* base = qkv_s + (size_t)wl * WR * RS;
+    op_t* base = qkv_s + (size_t)wl * WR * RS;
     const int qoff = h * HD, koff = C + h * HD, voff = 2 * C + h * HD;
     // ---- S = Q K^T ----
     float s[2][4][4];
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(WA_THREADS) window_attn_kernel(const WinAttnPa
       uint32_t a[2][4];
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
-        const __nv_bfloat16* qr = base + (mt * 16 + g) * RS + qoff + col;
+        const op_t* qr = base + (mt * 16 + g) * RS + qoff + col;
         a[mt][0] = col < HD ? *reinterpret_cast<const uint32_t*>(qr) : 0u;
         a[mt][1] = col < HD ? *reinterpret_cast<const uint32_t*>(qr + 8 * RS) : 0u;
         a[mt][2] = col + 8 < HD ? *reinterpret_cast<const uint32_t*>(qr + 8) : 0u;
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(WA_THREADS) window_attn_kernel(const WinAttnPa
       }
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
-        const __nv_bfloat16* kr = base + (nt * 8 + g) * RS + koff + col;
+        const op_t* kr = base + (nt * 8 + g) * RS + koff + col;
         const uint32_t b0 = col < HD ? *reinterpret_cast<const uint32_t*>(kr) : 0u;
         const uint32_t b1 = col + 8 < HD ? *reinterpret_cast<const uint32_t*>(kr + 8) : 0u;
         wa_mma(s[0][nt], a[0], b0, b1);
@@ -207,10 +207,10 @@ __global__ void __launch_bounds__(WA_THREADS) window_attn_kernel(const WinAttnPa
       uint32_t pa[2][4];
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
-        pa[mt][0] = pack_bf16(s[mt][2 * ks][0], s[mt][2 * ks][1]);
-        pa[mt][1] = pack_bf16(s[mt][2 * ks][2], s[mt][2 * ks][3]);
-        pa[mt][2] = pack_bf16(s[mt][2 * ks + 1][0], s[mt][2 * ks + 1][1]);
-        pa[mt][3] = pack_bf16(s[mt][2 * ks + 1][2], s[mt][2 * ks + 1][3]);
+        pa[mt][0] = pack_op(s[mt][2 * ks][0], s[mt][2 * ks][1]);
+        pa[mt][1] = pack_op(s[mt][2 * ks][2], s[mt][2 * ks][3]);
+        pa[mt][2] = pack_op(s[mt][2 * ks + 1][0], s[mt][2 * ks + 1][1]);
+        pa[mt][3] = pack_op(s[mt][2 * ks + 1][2], s[mt][2 * ks + 1][3]);
       }
       const uint32_t vrow = smem_u32(base + (ks * 16 + (lane & 15)) * RS + vcol0);
 #pragma unroll
@@ -229,9 +229,9 @@ __global__ void __launch_bounds__(WA_THREADS) window_attn_kernel(const WinAttnPa
       for (int n = 0; n < NTO; ++n) {
         const int dcol = n * 8 + t4 * 2 - (voff - vcol0);   // column inside the head
         if (dcol >= 0 && dcol < HD) {
-          __nv_bfloat16* orow = base + (mt * 16 + g) * RS + qoff + dcol;
-          *reinterpret_cast<uint32_t*>(orow) = pack_bf16(o[mt][n][0] * inv[mt][0], o[mt][n][1] * inv[mt][0]);
-          *reinterpret_cast<uint32_t*>(orow + 8 * RS) = pack_bf16(o[mt][n][2] * inv[mt][1], o[mt][n][3] * inv[mt][1]);
+          op_t* orow = base + (mt * 16 + g) * RS + qoff + dcol;
+          *reinterpret_cast<uint32_t*>(orow) = pack_op(o[mt][n][0] * inv[mt][0], o[mt][n][1] * inv[mt][0]);
+          *reinterpret_cast<uint32_t*>(orow + 8 * RS) = pack_op(o[mt][n][2] * inv[mt][1], o[mt][n][3] * inv[mt][1]);
         }
       }
   }
@@ -241,8 +241,8 @@ __global__ void __launch_bounds__(WA_THREADS) window_attn_kernel(const WinAttnPa
     const int wl = i / WN, t = i - wl * WN;
     const long long tok = tok_s[wl * WR + t];
     if (tok < 0) continue;
-    const __nv_bfloat16* src = qkv_s + (size_t)(wl * WR + t) * RS;
-    __nv_bfloat16* dst = p.out + tok * C;
+    const op_t* src = qkv_s + (size_t)(wl * WR + t) * RS;
+    op_t* dst = p.out + tok * C;
     if (C % 8 == 0) {
       for (int c = lane * 8; c < C; c += 256) *reinterpret_cast<uint4*>(dst + c) = *reinterpret_cast<const uint4*>(src + c);
     } else {

@@ -10,6 +10,11 @@ from ._lib import RowGemmArgs
 A_F32_LN, A_F32, A_BF16, A_MERGE_LN = 0, 1, 2, 3
 E_BF16, E_F32, E_EXPAND = 0, 1, 2
 
+def operand_dtype():
+    """16-bit tensor-core operand dtype of the loaded library (fp16 by default, bf16 with -DSWN_OPERAND_BF16=1)."""
+    return torch.bfloat16 if _lib.load().swn_operand_is_bf16() else torch.float16
+
+
 LAUNCH_COUNT = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
 _LAUNCHES_PER_CALL = {"swin_block_small": 1, "rowgemm": 1,"mlp": 1, "window_attention": 1, "cross_attention": 1, "patch_embed": 1,
                       "seg_head": 2, "recon_head": 1, "copy_cols": 1, "sigmoid_mask": 1, "sigmoid_mask_mm": 2,

@@ -7,15 +7,20 @@ no tensor maps are needed and the stream order is the MMA consumption order."""
 import torch
 
 
+def OPERAND_DTYPE():
+    from . import ops
+    return ops.operand_dtype()
+
+
 def ceil_to(x, m):
     return (x + m - 1) // m * m
 
 
-def swizzle_tiles(t: torch.Tensor) -> torch.Tensor:
-    """t: [..., R, 64] (any float dtype) -> bf16, same shape, 16-byte chunks XOR-permuted per row."""
+def swizzle_tiles(t: torch.Tensor, dtype=None) -> torch.Tensor:
+    """t: [..., R, 64] (any float dtype) -> 16-bit operand dtype, same shape, 16-byte chunks XOR-permuted per row."""
     R = t.shape[-2]
     assert t.shape[-1] == 64
-    t = t.to(torch.bfloat16).reshape(*t.shape[:-1], 8, 8)
+    t = t.to(dtype or OPERAND_DTYPE()).reshape(*t.shape[:-1], 8, 8)
     rows = torch.arange(R, device=t.device)
     idx = torch.arange(8, device=t.device)[None, :] ^ (rows[:, None] & 7)          # [R, 8]: out chunk j <- in chunk j^(r&7)
     idx = idx.view(*([1] * (t.dim() - 3)), R, 8, 1).expand(*t.shape)
@@ -24,7 +29,7 @@ def swizzle_tiles(t: torch.Tensor) -> torch.Tensor:
 
 def unswizzle_tiles(t: torch.Tensor) -> torch.Tensor:
     """inverse of swizzle_tiles (XOR is an involution) — used by the CPU layout tests."""
-    return swizzle_tiles(t.float()).to(t.dtype)
+    return swizzle_tiles(t.float(), t.dtype).to(t.dtype)
 
 
 def choose_chunk(N: int, max_nt: int = 256) -> int:

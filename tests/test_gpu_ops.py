@@ -14,6 +14,7 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 TOL_BF16 = 2e-2
 TOL_F32 = 1e-4
+OPD = S.ops.operand_dtype()   # 16-bit tensor-core operand dtype of the built library (fp16 default)
 
 
 def relerr(a, b):
@@ -24,7 +25,7 @@ def relerr(a, b):
 
 
 def bf(x):  # bf16 rounding of an operand, as the kernel sees it
-    return x.to(torch.bfloat16).float()
+    return x.to(OPD).float()
 
 
 def rnd(*shape, seed=0, scale=1.0):
@@ -41,7 +42,7 @@ def test_rowgemm_ln_qkv(C, M):
     ref = O.linear(O.layer_norm(x, lw, lb), W, b)
     nv = packing.choose_chunk(3 * C, 256)
     Wp, bp, NT, nch = packing.pack_rowgemm(W.to(DEV), b.to(DEV), nv)
-    out = torch.empty(M, 3 * C, device=DEV, dtype=torch.bfloat16)
+    out = torch.empty(M, 3 * C, device=DEV, dtype=OPD)
     ops.rowgemm(A=x.to(DEV), a_mode=ops.A_F32_LN, M=M, K=C, lda=C, ln_w=lw.to(DEV), ln_b=lb.to(DEV), Wp=Wp, NT=NT,
                 nchunks=nch, n_valid=nv, e_mode=ops.E_BF16, bias=bp, out=out, ldo=3 * C)
     torch.cuda.synchronize()
@@ -50,7 +51,7 @@ def test_rowgemm_ln_qkv(C, M):
 
 @pytest.mark.parametrize("C,M", [(48, 300), (192, 129), (384, 256), (12, 77)])
 def test_rowgemm_bf16_proj_residual_alpha(C, M):
-    a = rnd(M, C, seed=1).to(torch.bfloat16)
+    a = rnd(M, C, seed=1).to(OPD)
     W, b = rnd(C, C, seed=2, scale=C ** -0.5), rnd(C, seed=3, scale=0.1)
     res = rnd(M, C, seed=4)
     gamma = torch.tensor([0.37])
@@ -66,7 +67,7 @@ def test_rowgemm_bf16_proj_residual_alpha(C, M):
 
 def test_rowgemm_inplace_residual():
     C, M = 96, 200
-    a = rnd(M, C, seed=1).to(torch.bfloat16)
+    a = rnd(M, C, seed=1).to(OPD)
     W, b = rnd(C, C, seed=2, scale=C ** -0.5), rnd(C, seed=3, scale=0.1)
     x = rnd(M, C, seed=4)
     ref = x + O.linear(a.float(), W, b)
@@ -159,10 +160,10 @@ def _win_attn_ref(qkv, bias, table, B, H, W, C, nH, shift):
                                             (96, 3, 5, 5, 3)])
 def test_window_attention(C, nH, H, W, shift):
     B = 2
-    qkv = rnd(B * H * W, 3 * C, seed=1).to(torch.bfloat16)
+    qkv = rnd(B * H * W, 3 * C, seed=1).to(OPD)
     bias, table = rnd(3 * C, seed=2, scale=0.3), rnd(81, nH, seed=3, scale=0.5)
     ref = _win_attn_ref(qkv.float(), bf(bias), table, B, H, W, C, nH, shift)
-    out = torch.empty(B * H * W, C, device=DEV, dtype=torch.bfloat16)
+    out = torch.empty(B * H * W, C, device=DEV, dtype=OPD)
     ops.window_attention(qkv.to(DEV), out, bias.to(DEV), table.to(DEV), B, H, W, C, nH, shift)
     torch.cuda.synchronize()
     assert relerr(out, ref) <= 1e-2
@@ -172,13 +173,13 @@ def test_window_attention(C, nH, H, W, shift):
 def test_cross_attention_core(C, Lq, Lk):
     B, nH = 2, 3
     hd = C // nH
-    q = rnd(B, Lq, C, seed=1).to(torch.bfloat16)
-    kv = rnd(B, Lk, 2 * C, seed=2).to(torch.bfloat16)
+    q = rnd(B, Lq, C, seed=1).to(OPD)
+    kv = rnd(B, Lk, 2 * C, seed=2).to(OPD)
     Q = q.float().view(B, Lq, nH, hd).permute(0, 2, 1, 3)
     K = kv.float()[..., :C].reshape(B, Lk, nH, hd).permute(0, 2, 1, 3)
     V = kv.float()[..., C:].reshape(B, Lk, nH, hd).permute(0, 2, 1, 3)
     ref = (torch.softmax(Q @ K.transpose(-1, -2) * hd ** -0.5, -1) @ V).permute(0, 2, 1, 3).reshape(B, Lq, C)
-    out = torch.empty(B, Lq, C, device=DEV, dtype=torch.bfloat16)
+    out = torch.empty(B, Lq, C, device=DEV, dtype=OPD)
     ops.cross_attention(q.to(DEV), kv.to(DEV), out, B, Lq, Lk, C, nH)
     torch.cuda.synchronize()
     assert relerr(out, ref) <= 1.5e-2
@@ -281,8 +282,8 @@ def test_errors_are_loud():
         ops.rowgemm(A=torch.zeros(4, 6, device=DEV), a_mode=ops.A_F32, M=4, K=6, lda=6, Wp=torch.zeros(8, device=DEV),
                     NT=16, nchunks=1, n_valid=4, e_mode=ops.E_F32, out=torch.zeros(4, 4, device=DEV), ldo=4)
     with pytest.raises(RuntimeError):
-        ops.window_attention(torch.zeros(25, 30, device=DEV, dtype=torch.bfloat16),
-                             torch.zeros(25, 10, device=DEV, dtype=torch.bfloat16), torch.zeros(30, device=DEV),
+        ops.window_attention(torch.zeros(25, 30, device=DEV, dtype=OPD),
+                             torch.zeros(25, 10, device=DEV, dtype=OPD), torch.zeros(30, device=DEV),
                              torch.zeros(81, 1, device=DEV), 1, 5, 5, 10, 1, 0)   # head_dim 10 unsupported
     with pytest.raises(RuntimeError):
         S.SwinWNet(depths=[2, 2, 2, 2]).segment_1(torch.zeros(1, 1, 20, 20))    # CPU tensor: no fallback

@@ -13,6 +13,7 @@ from oracle import swinwnet_oracle as O
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 D2 = [2, 2, 2, 2]
+OPD = S.ops.operand_dtype()   # 16-bit tensor-core operand dtype of the built library (fp16 default)
 
 
 def test_library_exports_every_declared_symbol():
@@ -72,8 +73,8 @@ def test_pack_rowgemm_layout():
     W = torch.randn(N, K)
     b = torch.randn(N)
     Wp, bp, NT, nch = packing.pack_rowgemm(W, b, nv)
-    assert (NT, nch) == (144, 2) and Wp.dtype == torch.bfloat16 and Wp.numel() == nch * 2 * NT * 64
-    Wb = W.to(torch.bfloat16)
+    assert (NT, nch) == (144, 2) and Wp.dtype == OPD and Wp.numel() == nch * 2 * NT * 64
+    Wb = W.to(OPD)
     for (n, kb, r, k) in [(0, 0, 0, 0), (1, 1, 143, 31), (1, 0, 77, 63), (0, 1, 9, 17)]:
         assert _tile_element(Wp, NT, n * 2 + kb, r, k) == Wb[n * nv + r, kb * 64 + k]
     assert _tile_element(Wp, NT, 1, 5, 40) == 0          # k = 64+40 >= K: zero padding
@@ -92,7 +93,7 @@ def test_pack_mlp_stream_order():
     assert Wp.numel() == nj * (g1 + g2) and torch.equal(b2p, b2)
     # stream: G1(0) G1(1) G2(0) G1(2) G2(1) G2(2)
     off = {"g1_0": 0, "g1_1": g1, "g2_0": 2 * g1, "g1_2": 2 * g1 + g2, "g2_1": 3 * g1 + g2, "g2_2": 3 * g1 + 2 * g2}
-    W1b, W2b = W1.to(torch.bfloat16), W2.to(torch.bfloat16)
+    W1b, W2b = W1.to(OPD), W2.to(OPD)
     assert _tile_element(Wp[off["g1_2"]:], HC, 1, 100, 20) == W1b[2 * HC + 100, 64 + 20]
     assert _tile_element(Wp[off["g2_1"]:], TR, 1, 50, 7) == W2b[50, 1 * HC + 64 + 7]
     assert _tile_element(Wp[off["g2_0"]:], TR, 0, 95, 63) == W2b[95, 63]

@@ -17,9 +17,11 @@ ap.add_argument("--ops", default="mlp,qkv,proj,attn")
 ap.add_argument("--only", type=int, default=0)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--once", action="store_true")
+ap.add_argument("--inplace", action="store_true", help="out aliases x (as the model runs blocks)")
 a = ap.parse_args()
 DEV = "cuda"
 torch.manual_seed(0)
+OPD = S.ops.operand_dtype()   # 16-bit tensor-core operand dtype of the built library (fp16 default)
 # (tokens per image, C, heads, grid H, W)
 SHAPES = [(30000, 48, 3, 125, 240), (7560, 96, 6, 63, 120), (1920, 192, 12, 32, 60), (480, 384, 24, 16, 30),
           (1920, 384, 12, 32, 60), (7560, 192, 6, 63, 120), (30000, 96, 3, 125, 240), (120000, 24, 3, 250, 480),
@@ -67,29 +69,29 @@ for (L, C, nH, H, W) in SHAPES:
         W2, b2 = torch.randn(C, 4 * C, device=DEV) * (4 * C) ** -0.5, torch.zeros(C, device=DEV)
         HC, TR = ops.mlp_config(C)
         Wp, b2p = packing.pack_mlp(W1, W2, b2, HC, TR)
-        out = torch.empty_like(x)
+        out = x if a.inplace else torch.empty_like(x)
         ms = timeit(lambda: ops.mlp(x, out, M, C, lw, lb, Wp, b1, b2p))
         report("mlp", M, C, ms, M * C * 8, 16.0 * M * C * C)
     if "qkv" in a.ops:
         Wq, bq = torch.randn(3 * C, C, device=DEV) * C ** -0.5, torch.zeros(3 * C, device=DEV)
         nv = packing.choose_chunk(3 * C, 256)
         Wp, bp, NT, nch = packing.pack_rowgemm(Wq, bq, nv)
-        qkv = torch.empty(M, 3 * C, device=DEV, dtype=torch.bfloat16)
+        qkv = torch.empty(M, 3 * C, device=DEV, dtype=OPD)
         ms = timeit(lambda: ops.rowgemm(A=x, a_mode=ops.A_F32_LN, M=M, K=C, lda=C, ln_w=lw, ln_b=lb, Wp=Wp, NT=NT, nchunks=nch,
                                         n_valid=nv, e_mode=ops.E_BF16, bias=bp, out=qkv, ldo=3 * C))
         report("qkv", M, C, ms, M * C * 10, 6.0 * M * C * C)
     if "attn" in a.ops:
-        qkv = torch.randn(M, 3 * C, device=DEV).to(torch.bfloat16)
-        att = torch.empty(M, C, device=DEV, dtype=torch.bfloat16)
+        qkv = torch.randn(M, 3 * C, device=DEV).to(OPD)
+        att = torch.empty(M, C, device=DEV, dtype=OPD)
         bq, tab = torch.zeros(3 * C, device=DEV), torch.zeros(81, nH, device=DEV)
         ms = timeit(lambda: ops.window_attention(qkv, att, bq, tab, B, H, W, C, nH, 0))
         report("attn", M, C, ms, M * C * 8, 100.0 * M * C)
     if "proj" in a.ops:
-        att = torch.randn(M, C, device=DEV).to(torch.bfloat16)
+        att = torch.randn(M, C, device=DEV).to(OPD)
         Wo, bo = torch.randn(C, C, device=DEV) * C ** -0.5, torch.zeros(C, device=DEV)
         nv = packing.choose_chunk(C, 256)
         Wp, bp, NT, nch = packing.pack_rowgemm(Wo, bo, nv)
-        out = torch.empty_like(x)
+        out = x if a.inplace else torch.empty_like(x)
         ms = timeit(lambda: ops.rowgemm(A=att, a_mode=ops.A_BF16, M=M, K=C, lda=C, Wp=Wp, NT=NT, nchunks=nch, n_valid=nv,
                                         e_mode=ops.E_F32, bias=bp, out=out, ldo=C, res=x, ldres=C))
         report("proj", M, C, ms, M * C * 10, 2.0 * M * C * C)

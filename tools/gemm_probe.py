@@ -11,6 +11,7 @@ from swinwnet_b200 import ops, packing  # noqa: E402
 
 torch.manual_seed(0)
 DEV = "cuda"
+OPD = S.ops.operand_dtype()   # 16-bit tensor-core operand dtype of the built library (fp16 default)
 
 
 def report(name, out, ref):
@@ -35,9 +36,9 @@ def report(name, out, ref):
 
 def gemm_case(M, K, N, nv=None):
     nv = nv or packing.choose_chunk(N, 256)
-    a = torch.randn(M, K).to(torch.bfloat16)
+    a = torch.randn(M, K).to(OPD)
     W = torch.randn(N, K) * K ** -0.5
-    ref = a.float() @ W.to(torch.bfloat16).float().t()
+    ref = a.float() @ W.to(OPD).float().t()
     Wp, _, NT, nch = packing.pack_rowgemm(W.to(DEV), None, nv)
     out = torch.zeros(M, N, device=DEV)
     ops.rowgemm(A=a.to(DEV), a_mode=ops.A_BF16, M=M, K=K, lda=K, Wp=Wp, NT=NT, nchunks=nch, n_valid=nv, e_mode=ops.E_F32,
