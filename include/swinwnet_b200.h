@@ -72,6 +72,13 @@ int swn_mlp(const float* x, float* out, int M, int C, const float* ln_w, const f
 int swn_swin_block_small(const float* x, float* out, int B, int H, int W, int C, int num_heads, int shift, float eps,
                          const float* const* w, void* stream);
 
+/* One whole SwinTransformerBlock with shift_size 0 (SwinWNet.py:236-280), or only its attention half
+ * x + proj(W-MSA(LayerNorm1(x))) when do_mlp == 0, as ONE tcgen05 kernel for C <= 64: window partition / reverse /
+ * padding are index math, q/k/v, probabilities and the hidden activation never leave the SM.
+ * Wpk / fpk = packed 16-bit weight images and fp32 vectors, see packing.py::pack_fused_block.  out must not alias x. */
+int swn_swin_block_fused(const float* x, float* out, int B, int H, int W, int C, int num_heads, float eps,
+                         const void* Wpk, const float* fpk, int do_mlp, void* stream);
+
 /* 5x5 (shifted-)window attention core on token-ordered qkv (SwinWNet.py:86-149,183-206,246-272). */
 int swn_window_attention(const void* qkv_bf16, void* out_bf16, const float* qkv_bias, const float* rpb_table,
                          int B, int H, int W, int C, int num_heads, int shift, void* stream);

@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libswinwnet_b200.so")
-SOURCES = ["api.cu", "rowgemm.cu", "rowgemm_persist.cu","mlp.cu", "mlp_persist.cu", "window_attn.cu", "small_block.cu", "cross_attn.cu", "elementwise.cu"]
+SOURCES = ["api.cu", "rowgemm.cu", "rowgemm_persist.cu","mlp.cu", "mlp_persist.cu", "window_attn.cu", "small_block.cu", "swin_fused.cu", "cross_attn.cu", "elementwise.cu"]
 HEADERS = ["common.cuh", "kernels.h", os.path.join("..", "..", "include", "swinwnet_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

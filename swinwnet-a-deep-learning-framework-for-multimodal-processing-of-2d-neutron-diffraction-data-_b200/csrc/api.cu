@@ -93,6 +93,16 @@ int swn_swin_block_small(const float* x, float* out, int B, int H, int W, int C,
   return launch_swin_block_small(p, num_sms(), reinterpret_cast<cudaStream_t>(stream));
 }
 
+int swn_swin_block_fused(const float* x, float* out, int B, int H, int W, int C, int num_heads, float eps,
+                         const void* Wpk, const float* fpk, int do_mlp, void* stream) {
+  SWN_CHECK(x && out && Wpk && fpk, "swin_block_fused: null pointer");
+  SWN_CHECK(x != out, "swin_block_fused: out must not alias x");
+  FusedBlockParams p{};
+  p.x = x; p.out = out; p.B = B; p.H = H; p.W = W; p.C = C; p.nH = num_heads; p.eps = eps;
+  p.Wpk = reinterpret_cast<const op_t*>(Wpk); p.fpk = fpk; p.do_mlp = do_mlp;
+  return launch_swin_fused(p, num_sms(), reinterpret_cast<cudaStream_t>(stream));
+}
+
 int swn_window_attention(const void* qkv, void* out, const float* qkv_bias, const float* rpb_table, int B, int H, int W,
                          int C, int num_heads, int shift, void* stream) {
   SWN_CHECK(qkv && out && qkv_bias && rpb_table, "window_attention: null pointer");

@@ -81,6 +81,25 @@ struct SmallBlockParams {   // one whole SwinTransformerBlock, C in {12, 24}, fp
 };
 int launch_swin_block_small(SmallBlockParams p, int num_sms, cudaStream_t stream);
 
+// ---- swin_fused.cu --------------------------------------------------------------------------
+struct FusedBlockParams {   // fused W-MSA (+ MLP) block, shift 0, resident packed weights (packing.py::pack_fused_block)
+  const float* x;     // [B, H*W, C] fp32
+  float* out;         // [B, H*W, C] fp32 (must not alias x: tiles are read by prefetch while others are written)
+  int B, H, W, C, nH;
+  float eps;
+  const op_t* Wpk;    // [Wqkv | Wproj | W1 chunks | W2 chunks] as SWIZZLE_128B k-block images
+  const float* fpk;   // bqkv' bqkv bproj b1' b2 bias-fragment images (see packing.py)
+  int do_mlp;         // 1: whole block, 0: attention half only (x + proj(attn(LN1 x)))
+  // filled in by the launcher
+  int K16, NQ, HC, nj, n_hs, n_stage, ones_col, RS, RSB;
+  int nWy, nWx, ntiles;
+  long long n_windows;
+  int w_bytes, nf, u_bytes;
+  int off_a, off_u, off_stage, off_f, off_misc;
+  int tm_y, tmem_cols;
+};
+int launch_swin_fused(FusedBlockParams p, int num_sms, cudaStream_t stream);
+
 // ---- cross_attn.cu --------------------------------------------------------------------------
 struct CrossAttnParams {
   const op_t* q;   // [B, Lq, C]

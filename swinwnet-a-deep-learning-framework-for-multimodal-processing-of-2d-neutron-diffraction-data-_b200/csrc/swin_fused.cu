@@ -1,0 +1,638 @@
+// Fused W-MSA / whole SwinTransformerBlock kernel (shift_size = 0, 5x5 windows; SwinWNet.py:183-209, 236-280):
+//
+//   x -> LN1 -> qkv (tcgen05) -> per-(window, head) softmax(q k^T + rel-pos bias) v (mma.sync on smem tiles)
+//     -> proj (tcgen05) -> + x  [-> LN2 -> fc1 (tcgen05) -> GELU -> fc2 (tcgen05) -> +]  -> out
+//
+// A tile is 5 consecutive windows = 125 tokens (rows wl*25 + t of a 128-row UMMA tile), so window_partition /
+// window_reverse / zero padding are pure index math on the cp.async gather and the coalesced write-back; q, k, v,
+// the attention probabilities, the attention output and the 4C-wide hidden activation never leave the SM.  HBM
+// traffic is one fp32 read and one fp32 write of the token rows (8C bytes / token) for the whole block.
+//
+// Weights of the block (16-bit, pre-swizzled UMMA K-major SWIZZLE_128B images, packing.py::pack_fused_block) are
+// loaded once per persistent CTA with bulk copies and stay resident in shared memory.  All phases of a tile are
+// executed by all warps (epilogues split TMEM lane groups x column parts), MMAs are issued by one elected lane of
+// warp 0 and tracked with mbarriers; the next tile's rows are prefetched with cp.async while the current tile
+// computes.  Latency of the serial phase chain is hidden by co-resident CTAs (C <= 24) or by the prefetch.
+//
+// Semantics kept from the reference: the window zero padding happens AFTER norm1 (padded tokens are exact zero
+// vectors, their q/k/v equal the qkv bias, they take part as keys; SwinWNet.py:242-255), q is scaled by hd^-0.5
+// (folded into the packed q rows / bias together with log2(e)), the relative-position bias is added unscaled.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace swn {
+
+namespace {
+
+constexpr int FB_WIN = 5, FB_TOK = 25;
+
+__device__ __forceinline__ void fb_mma(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32." SWN_MMA_T "." SWN_MMA_T ".f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void fb_ldsm_x2_trans(uint32_t& r0, uint32_t& r1, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+
+// P = 2^(s - m) as a packed 16-bit pair (the A fragment of the P V mma)
+__device__ __forceinline__ uint32_t fb_exp2_pack(float a, float b, float m) {
+  return pack_op(ex2_approx(a - m), ex2_approx(b - m));
+}
+
+struct FbBars {
+  uint64_t w, mma, g1[2], g2[2];
+  uint32_t tmem_base;
+};
+
+}  // namespace
+
+template <int HD, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockParams p) {
+  constexpr int NP = NT / 128;               // column parts per TMEM lane group
+  constexpr int KS = HD >= 16 ? HD / 16 : 1;   // k-steps of S = Q K^T
+  constexpr int NTO = HD >= 8 ? HD / 8 : 1;    // 8-wide output column tiles of O = P V
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+
+  const int C = p.C, K16 = p.K16, NQ = p.NQ, HC = p.HC, nj = p.nj, nH = p.nH, RS = p.RS, RSB = p.RSB;
+  const int C4 = C >> 2, KB = (K16 + 63) >> 6, ksteps = K16 >> 4;
+  // ---- shared memory carve-up (offsets computed by the launcher) ----
+  uint8_t* wq_s = smem;                                   // [KB][NQ x 64]
+  uint8_t* wp_s = wq_s + KB * NQ * 128;                   // [KB][K16 x 64]
+  uint8_t* w1_s = wp_s + KB * K16 * 128;                  // [nj][KB][HC x 64]
+  uint8_t* w2_s = w1_s + nj * KB * HC * 128;              // [nj][K16 x 64]
+  uint8_t* a_s = smem + p.off_a;                          // A tile: [KB][128 x 64]
+  uint8_t* u_s = smem + p.off_u;                          // qkv rows [132][RS]  |  hidden tiles [n_hs][128 x 64]
+  uint8_t* stg = smem + p.off_stage;                      // [2][128][RSB] fp32 token rows (x, then x1, then out)
+  float* f_s = reinterpret_cast<float*>(smem + p.off_f);
+  const float* bqkv = f_s;                                // [NQ]  qkv bias with norm1's affine folded in (+ ones block)
+  const float* bqkv_pad = bqkv + NQ;                      // [NQ]  plain qkv bias: q/k/v of zero-padded tokens
+  const float* bproj = bqkv_pad + NQ;                     // [K16]
+  const float* b1 = bproj + K16;                          // [4C]  fc1 bias with norm2's affine folded in
+  const float* b2 = b1 + 4 * C;                           // [K16]
+  const float4* biasfrag = reinterpret_cast<const float4*>(b2 + K16);   // [nH][8][32] accumulator-fragment bias images
+  int* tok_s = reinterpret_cast<int*>(smem + p.off_misc);             // [3][128]
+  float2* red = reinterpret_cast<float2*>(tok_s + 3 * 128);           // [NP][128]
+  FbBars* bars = reinterpret_cast<FbBars*>(red + NP * 128);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = tid & 127, part = tid >> 7;
+  const int g = lane >> 2, t4 = lane & 3;
+
+  if (tid == 0) {
+    mbar_init(&bars->w, 1);
+    mbar_init(&bars->mma, 1);
+    mbar_init(&bars->g1[0], 1);
+    mbar_init(&bars->g1[1], 1);
+    mbar_init(&bars->g2[0], 1);
+    mbar_init(&bars->g2[1], 1);
+    fence_barrier_init();
+  }
+  for (int i = tid * 16; i < KB * A_KBLOCK_BYTES; i += NT * 16) *reinterpret_cast<uint4*>(a_s + i) = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid * 16; i < p.u_bytes; i += NT * 16) *reinterpret_cast<uint4*>(u_s + i) = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid; i < p.nf; i += NT) f_s[i] = p.fpk[i];
+  if (warp == 0) tmem_alloc(&bars->tmem_base, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+  const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+  if (tid == 0) {
+    // resident weights: one expect_tx, bulk copies of <= 16 KB
+    mbar_arrive_expect_tx(&bars->w, (uint32_t)p.w_bytes);
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(p.Wpk);
+    for (int o = 0; o < p.w_bytes; o += 16384) bulk_g2s(smem + o, src + o, (uint32_t)min(16384, p.w_bytes - o), &bars->w);
+  }
+
+  const uint32_t idesc_q = umma_idesc_bf16(TILE_M, (uint32_t)(NQ > 256 ? NQ / 2 : NQ));
+  const uint32_t idesc_c = umma_idesc_bf16(TILE_M, (uint32_t)K16);
+  const uint32_t idesc_h = umma_idesc_bf16(TILE_M, (uint32_t)HC);
+  const uint64_t a_desc = umma_desc_sw128(smem_u32(a_s));
+  const int HCp = (HC + 31) & ~31;
+  const int nWin2 = p.nWy * p.nWx;
+
+  auto calc_tok = [&](int tile, int slot) {
+    if (tid < 128) {
+      int tok = -1;
+      const int wl = tid / FB_TOK, t = tid - wl * FB_TOK;
+      const long long w = (long long)tile * FB_WIN + wl;
+      if (wl < FB_WIN && w < p.n_windows) {
+        const int b = (int)(w / nWin2);
+        const int wr = (int)(w - (long long)b * nWin2);
+        const int wy = wr / p.nWx, wx = wr - wy * p.nWx;
+        const int Y = wy * 5 + t / 5, X = wx * 5 + t % 5;
+        if (Y < p.H && X < p.W) tok = (b * p.H + Y) * p.W + X;
+      }
+      tok_s[slot * 128 + tid] = tok;
+    }
+  };
+  // 16-byte chunk q = tid + i*NT of the [128 x C] tile <-> (row, chunk-in-row), advanced without divisions
+  const int ch_r0 = tid / C4, ch_c0 = tid - ch_r0 * C4, ch_rstep = NT / C4, ch_cstep = NT - ch_rstep * C4;
+  auto issue_loads = [&](int slot, int buf) {
+    const uint32_t dst0 = smem_u32(stg + buf * 128 * RSB);
+    int r = ch_r0, c4 = ch_c0;
+    while (r < 128) {
+      const int tok = tok_s[slot * 128 + r];
+      const float* src = tok >= 0 ? p.x + (long long)tok * C + c4 * 4 : p.x;
+      cp_async16(dst0 + r * RSB + c4 * 16, src, tok >= 0 ? 16u : 0u);
+      c4 += ch_cstep;
+      r += ch_rstep;
+      if (c4 >= C4) {
+        c4 -= C4;
+        ++r;
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  // (x - mean) * rstd of the staged rows -> 16-bit A tile (the LayerNorm affine is folded into the packed weights;
+  // rows of invalid tokens are exact zeros)
+  auto normalize_rows = [&](const uint8_t* srow, float mean, float rstd, bool valid) {
+    const float nm = -mean * rstd;
+    for (int u = part; u < (K16 >> 3); u += NP) {
+      uint32_t pk[4] = {0u, 0u, 0u, 0u};
+      if (valid) {
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int c = u * 8 + hh * 4;
+          if (c < C) {
+            const float4 v = *reinterpret_cast<const float4*>(srow + c * 4);
+            pk[hh * 2] = pack_op(fmaf(v.x, rstd, nm), fmaf(v.y, rstd, nm));
+            pk[hh * 2 + 1] = pack_op(fmaf(v.z, rstd, nm), fmaf(v.w, rstd, nm));
+          }
+        }
+      }
+      const int k = u * 8;
+      *reinterpret_cast<uint4*>(a_s + (k >> 6) * A_KBLOCK_BYTES + sw128_offset(row, k & 63)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+  };
+
+  // phase parities of the mbarriers, one bit each (0: mma, 1-2: g1[0..1], 3-4: g2[0..1]); every completed phase of
+  // every barrier is waited for exactly once by every thread, so the bits stay in step with the barriers
+  uint32_t phases = 0;
+  auto wait_bar = [&](uint64_t* bar, int bit) {   // warp 0 polls the mbarrier, the CTA barrier releases everybody else
+    if (warp == 0) mbar_wait(bar, (phases >> bit) & 1u);
+    phases ^= 1u << bit;
+  };
+  const float inv_c = 1.0f / (float)C;
+  int it = 0;
+  const bool prefetch = p.n_stage == 2;
+  calc_tok(blockIdx.x, 0);     // grid <= ntiles
+  __syncthreads();
+  if (prefetch) issue_loads(0, 0);
+
+  for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+    const int buf = prefetch ? (it & 1) : 0, slot = it % 3;
+    const int next = tile + gridDim.x;
+    const bool has_next = next < p.ntiles;
+    if (has_next) calc_tok(next, (it + 1) % 3);
+    __syncthreads();   // previous tile's write-back finished everywhere; tok of the next tile visible
+    if (prefetch) {
+      if (has_next) {
+        issue_loads((it + 1) % 3, buf ^ 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+    } else {
+      issue_loads(slot, 0);
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();   // this tile's rows are in stg[buf]
+
+    uint8_t* stile = stg + buf * 128 * RSB;
+    uint8_t* srow = stile + row * RSB;
+    const int tokr = tok_s[slot * 128 + row];
+    const float x0 = *reinterpret_cast<const float*>(srow);
+
+    // ---------------- LN1 ----------------
+    {
+      float s1 = 0.f, s2 = 0.f;
+      for (int c = part * 4; c < C; c += NP * 4) {
+        const float4 v = *reinterpret_cast<const float4*>(srow + c * 4);
+        const float d0 = v.x - x0, d1 = v.y - x0, d2 = v.z - x0, d3 = v.w - x0;
+        s1 += (d0 + d1) + (d2 + d3);
+        s2 = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, s2))));
+      }
+      red[part * 128 + row] = make_float2(s1, s2);
+    }
+    __syncthreads();
+    {
+      float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+      for (int pp = 0; pp < NP; ++pp) {
+        const float2 r2 = red[pp * 128 + row];
+        t1 += r2.x;
+        t2 += r2.y;
+      }
+      const float m1 = t1 * inv_c;
+      const float rstd = rsqrtf(fmaxf(t2 * inv_c - m1 * m1, 0.f) + p.eps);
+      normalize_rows(srow, x0 + m1, rstd, tokr >= 0);
+    }
+    fence_proxy_async();
+    __syncthreads();
+
+    // ---------------- qkv = LN1(x) Wqkv^T  (TMEM columns [0, NQ)) ----------------
+    if (warp == 0) {
+      if (it == 0) mbar_wait(&bars->w, 0u);
+      tc_fence_after();
+      if (elect_one()) {
+        const int nchunk = NQ > 256 ? 2 : 1, ncols = NQ / nchunk;
+        for (int ch = 0; ch < nchunk; ++ch)
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t ad = a_desc + (uint64_t)((k >> 2) * (A_KBLOCK_BYTES >> 4) + (k & 3) * 2);
+            const uint64_t bd = umma_desc_sw128(smem_u32(wq_s + (k >> 2) * NQ * 128 + ch * ncols * 128)) + (uint64_t)((k & 3) * 2);
+            umma_bf16(tmem_base + (uint32_t)(ch * ncols), ad, bd, idesc_q, k != 0 ? 1u : 0u);
+          }
+        umma_commit(&bars->mma);
+      }
+      __syncwarp();
+    }
+    wait_bar(&bars->mma, 0);
+    __syncthreads();
+    tc_fence_after();
+    {
+      op_t* qrow = reinterpret_cast<op_t*>(u_s) + row * RS;
+      float v[16];
+      for (int cu = part; cu < (NQ >> 4); cu += NP) {
+        tmem_ld16(lane_addr + (uint32_t)(cu * 16), v);
+        tmem_ld_wait();
+        const float* bb = (tokr >= 0 ? bqkv : bqkv_pad) + cu * 16;
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pk[i] = pack_op(v[2 * i] + bb[2 * i], v[2 * i + 1] + bb[2 * i + 1]);
+        *reinterpret_cast<uint4*>(qrow + cu * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(qrow + cu * 16 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+
+    // ---------------- window attention core: one (window, head) pair per warp pass ----------------
+    for (int pr = warp; pr < FB_WIN * nH; pr += NT / 32) {
+      const int wl = pr / nH, h = pr - wl * nH;
+      if ((long long)tile * FB_WIN + wl >= p.n_windows) continue;
+      const op_t* base = reinterpret_cast<const op_t*>(u_s) + wl * FB_TOK * RS;
+      const int qoff = h * HD, koff = C + h * HD, voff = 2 * C + h * HD;
+      // accumulators start from the relative-position bias image of this head (log2 domain, -1e30 on the key columns
+      // 25..31 that belong to the next window / padding): the softmax argument comes straight out of the mma
+      float s[2][4][4];
+      {
+        const float4* bf = biasfrag + h * 256 + lane;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) {
+            const float4 b4 = bf[(mt * 4 + nt) * 32];
+            s[mt][nt][0] = b4.x; s[mt][nt][1] = b4.y; s[mt][nt][2] = b4.z; s[mt][nt][3] = b4.w;
+          }
+      }
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const int col = ks * 16 + t4 * 2;
+        uint32_t a[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          const op_t* qr = base + (mt * 16 + g) * RS + qoff + col;
+          a[mt][0] = col < HD ? *reinterpret_cast<const uint32_t*>(qr) : 0u;
+          a[mt][1] = col < HD ? *reinterpret_cast<const uint32_t*>(qr + 8 * RS) : 0u;
+          a[mt][2] = col + 8 < HD ? *reinterpret_cast<const uint32_t*>(qr + 8) : 0u;
+          a[mt][3] = col + 8 < HD ? *reinterpret_cast<const uint32_t*>(qr + 8 * RS + 8) : 0u;
+        }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const op_t* kr = base + (nt * 8 + g) * RS + koff + col;
+          const uint32_t b0 = col < HD ? *reinterpret_cast<const uint32_t*>(kr) : 0u;
+          const uint32_t b1 = col + 8 < HD ? *reinterpret_cast<const uint32_t*>(kr + 8) : 0u;
+          fb_mma(s[0][nt], a[0], b0, b1);
+          fb_mma(s[1][nt], a[1], b0, b1);
+        }
+      }
+      // P = 2^(s - rowmax) as 16-bit A fragments; the row sums come out of the P V mma through the ones block of qkv_s
+      uint32_t pa[2][2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        float m0 = fmaxf(fmaxf(s[mt][0][0], s[mt][0][1]), fmaxf(s[mt][1][0], s[mt][1][1]));
+        m0 = fmaxf(m0, fmaxf(fmaxf(s[mt][2][0], s[mt][2][1]), fmaxf(s[mt][3][0], s[mt][3][1])));
+        float m1 = fmaxf(fmaxf(s[mt][0][2], s[mt][0][3]), fmaxf(s[mt][1][2], s[mt][1][3]));
+        m1 = fmaxf(m1, fmaxf(fmaxf(s[mt][2][2], s[mt][2][3]), fmaxf(s[mt][3][2], s[mt][3][3])));
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          pa[mt][ks][0] = fb_exp2_pack(s[mt][2 * ks][0], s[mt][2 * ks][1], m0);
+          pa[mt][ks][1] = fb_exp2_pack(s[mt][2 * ks][2], s[mt][2 * ks][3], m1);
+          pa[mt][ks][2] = fb_exp2_pack(s[mt][2 * ks + 1][0], s[mt][2 * ks + 1][1], m0);
+          pa[mt][ks][3] = fb_exp2_pack(s[mt][2 * ks + 1][2], s[mt][2 * ks + 1][3], m1);
+        }
+      }
+      // O = P V  (+ one extra 8-column tile of ones: its accumulator is the softmax denominator of the row)
+      const int vcol0 = voff & ~7;
+      float o[2][NTO][4], od[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        od[mt][0] = od[mt][1] = od[mt][2] = od[mt][3] = 0.f;
+#pragma unroll
+        for (int n = 0; n < NTO; ++n) o[mt][n][0] = o[mt][n][1] = o[mt][n][2] = o[mt][n][3] = 0.f;
+      }
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const uint32_t vrow = smem_u32(base + (ks * 16 + (lane & 15)) * RS);
+        uint32_t b0, b1;
+#pragma unroll
+        for (int n = 0; n < NTO; ++n) {
+          fb_ldsm_x2_trans(b0, b1, vrow + (vcol0 + n * 8) * 2);
+          fb_mma(o[0][n], pa[0][ks], b0, b1);
+          fb_mma(o[1][n], pa[1][ks], b0, b1);
+        }
+        fb_ldsm_x2_trans(b0, b1, vrow + p.ones_col * 2);
+        fb_mma(od[0], pa[0][ks], b0, b1);
+        fb_mma(od[1], pa[1][ks], b0, b1);
+      }
+      float inv[2][2];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        inv[mt][0] = rcp_approx(od[mt][0]);
+        inv[mt][1] = rcp_approx(od[mt][2]);
+      }
+      // normalised O -> A tile (16-bit, swizzled), rows wl*25 + i, columns h*HD + d
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int n = 0; n < NTO; ++n) {
+          const int dcol = n * 8 + t4 * 2 - (voff - vcol0);
+          if (dcol >= 0 && dcol < HD) {
+            const int k = qoff + dcol;
+            const int i0 = mt * 16 + g, i1 = i0 + 8;
+            uint8_t* kb = a_s + (k >> 6) * A_KBLOCK_BYTES;
+            if (i0 < FB_TOK)
+              *reinterpret_cast<uint32_t*>(kb + sw128_offset(wl * FB_TOK + i0, k & 63)) = pack_op(o[mt][n][0] * inv[mt][0], o[mt][n][1] * inv[mt][0]);
+            if (i1 < FB_TOK)
+              *reinterpret_cast<uint32_t*>(kb + sw128_offset(wl * FB_TOK + i1, k & 63)) = pack_op(o[mt][n][2] * inv[mt][1], o[mt][n][3] * inv[mt][1]);
+          }
+        }
+    }
+    fence_proxy_async();
+    __syncthreads();
+
+    // ---------------- proj: Y = O Wproj^T (TMEM columns [tm_y, tm_y + K16)) ----------------
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+        for (int k = 0; k < ksteps; ++k) {
+          const uint64_t ad = a_desc + (uint64_t)((k >> 2) * (A_KBLOCK_BYTES >> 4) + (k & 3) * 2);
+          const uint64_t bd = umma_desc_sw128(smem_u32(wp_s + (k >> 2) * K16 * 128)) + (uint64_t)((k & 3) * 2);
+          umma_bf16(tmem_base + (uint32_t)p.tm_y, ad, bd, idesc_c, k != 0 ? 1u : 0u);
+        }
+        umma_commit(&bars->mma);
+      }
+      __syncwarp();
+    }
+    wait_bar(&bars->mma, 0);
+    __syncthreads();
+    tc_fence_after();
+    {
+      // x1 = x + proj + bias, written back to the staging row; partial LN2 moments on the fly
+      float s1 = 0.f, s2 = 0.f;
+      float v[16];
+      for (int cu = part; cu < (K16 >> 4); cu += NP) {
+        tmem_ld16(lane_addr + (uint32_t)(p.tm_y + cu * 16), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j4 = 0; j4 < 16; j4 += 4) {
+          const int c = cu * 16 + j4;
+          if (c < C) {
+            const float4 xr = *reinterpret_cast<const float4*>(srow + c * 4);
+            const float4 bb = *reinterpret_cast<const float4*>(bproj + c);
+            float4 o4;
+            o4.x = xr.x + v[j4 + 0] + bb.x;
+            o4.y = xr.y + v[j4 + 1] + bb.y;
+            o4.z = xr.z + v[j4 + 2] + bb.z;
+            o4.w = xr.w + v[j4 + 3] + bb.w;
+            *reinterpret_cast<float4*>(srow + c * 4) = o4;
+            const float d0 = o4.x - x0, d1 = o4.y - x0, d2 = o4.z - x0, d3 = o4.w - x0;
+            s1 += (d0 + d1) + (d2 + d3);
+            s2 = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, s2))));
+          }
+        }
+      }
+      red[part * 128 + row] = make_float2(s1, s2);
+    }
+    tc_fence_before();
+    __syncthreads();
+
+    if (p.do_mlp) {
+      // ---------------- LN2 ----------------
+      {
+        float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+        for (int pp = 0; pp < NP; ++pp) {
+          const float2 r2 = red[pp * 128 + row];
+          t1 += r2.x;
+          t2 += r2.y;
+        }
+        const float m1 = t1 * inv_c;
+        const float rstd = rsqrtf(fmaxf(t2 * inv_c - m1 * m1, 0.f) + p.eps);
+        normalize_rows(srow, x0 + m1, rstd, true);
+      }
+      fence_proxy_async();
+      __syncthreads();
+
+      // ---------------- MLP: hidden chunks of HC columns; GEMM1(j+1) is in flight during the GELU epilogue of j --------
+      auto issue_g1 = [&](int j) {
+        if (warp == 0) {
+          tc_fence_after();
+          if (elect_one()) {
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t ad = a_desc + (uint64_t)((k >> 2) * (A_KBLOCK_BYTES >> 4) + (k & 3) * 2);
+              const uint64_t bd = umma_desc_sw128(smem_u32(w1_s + (j * KB + (k >> 2)) * HC * 128)) + (uint64_t)((k & 3) * 2);
+              umma_bf16(tmem_base + (uint32_t)((j & 1) * HCp), ad, bd, idesc_h, k != 0 ? 1u : 0u);
+            }
+            umma_commit(&bars->g1[j & 1]);
+          }
+          __syncwarp();
+        }
+      };
+      issue_g1(0);
+      int last_hb = 0;
+      for (int j = 0; j < nj; ++j) {
+        if (j + 1 < nj) issue_g1(j + 1);
+        const int hb = p.n_hs == 2 ? (j & 1) : 0;
+        wait_bar(&bars->g1[j & 1], 1 + (j & 1));
+        if (j >= p.n_hs) wait_bar(&bars->g2[hb], 3 + hb);   // the hidden tile buffer is free once GEMM2(j - n_hs) retired
+        __syncthreads();
+        tc_fence_after();
+        uint8_t* hs = u_s + hb * A_KBLOCK_BYTES;
+        {
+          float v[16];
+          const float* bj = b1 + j * HC;
+          for (int cu = part; cu < (HC >> 4); cu += NP) {
+            tmem_ld16(lane_addr + (uint32_t)((j & 1) * HCp + cu * 16), v);
+            tmem_ld_wait();
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              pk[i] = pack_op(gelu_fast(v[2 * i] + bj[cu * 16 + 2 * i]), gelu_fast(v[2 * i + 1] + bj[cu * 16 + 2 * i + 1]));
+            *reinterpret_cast<uint4*>(hs + sw128_offset(row, cu * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(hs + sw128_offset(row, cu * 16 + 8)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+        }
+        tc_fence_before();
+        fence_proxy_async();
+        __syncthreads();
+        if (warp == 0) {
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t hd0 = umma_desc_sw128(smem_u32(hs));
+            const uint64_t bd0 = umma_desc_sw128(smem_u32(w2_s + j * K16 * 128));
+            for (int k = 0; k < (HC >> 4); ++k)
+              umma_bf16(tmem_base + (uint32_t)p.tm_y, hd0 + (uint64_t)(2 * k), bd0 + (uint64_t)(2 * k), idesc_c, (j | k) != 0 ? 1u : 0u);
+            umma_commit(&bars->g2[hb]);
+          }
+          __syncwarp();
+        }
+        last_hb = hb;
+      }
+      // drain the GEMM2 commits that nobody waited for yet (every phase of every barrier is observed exactly once)
+      {
+        const int pending0 = p.n_hs == 2 ? min(nj, 2) : 1;
+        if (pending0 == 2) {
+          const int other = last_hb ^ 1;
+          wait_bar(&bars->g2[other], 3 + other);
+        }
+        wait_bar(&bars->g2[last_hb], 3 + last_hb);
+      }
+      __syncthreads();
+      tc_fence_after();
+      {
+        float v[16];
+        for (int cu = part; cu < (K16 >> 4); cu += NP) {
+          tmem_ld16(lane_addr + (uint32_t)(p.tm_y + cu * 16), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j4 = 0; j4 < 16; j4 += 4) {
+            const int c = cu * 16 + j4;
+            if (c < C) {
+              const float4 xr = *reinterpret_cast<const float4*>(srow + c * 4);
+              const float4 bb = *reinterpret_cast<const float4*>(b2 + c);
+              *reinterpret_cast<float4*>(srow + c * 4) =
+                  make_float4(xr.x + v[j4 + 0] + bb.x, xr.y + v[j4 + 1] + bb.y, xr.z + v[j4 + 2] + bb.z, xr.w + v[j4 + 3] + bb.w);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncthreads();
+    }
+
+    // ---------------- coalesced write-back of the valid token rows ----------------
+    {
+      int r = ch_r0, c4 = ch_c0;
+      while (r < 128) {
+        const int tok = tok_s[slot * 128 + r];
+        if (tok >= 0)
+          *reinterpret_cast<float4*>(p.out + (long long)tok * C + c4 * 4) = *reinterpret_cast<const float4*>(stile + r * RSB + c4 * 16);
+        c4 += ch_cstep;
+        r += ch_rstep;
+        if (c4 >= C4) {
+          c4 -= C4;
+          ++r;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+int launch_swin_fused(FusedBlockParams p, int num_sms, cudaStream_t stream) {
+  const int C = p.C;
+  SWN_CHECK(p.B > 0 && p.H > 0 && p.W > 0 && C >= 4 && C % 4 == 0 && C <= 48 && p.nH > 0 && C % p.nH == 0,
+            "swin_fused: unsupported C=%d nH=%d", C, p.nH);
+  const int hd = C / p.nH;
+  SWN_CHECK(hd == 4 || hd == 8 || hd == 16 || hd == 32, "swin_fused: unsupported head_dim %d", hd);
+  SWN_CHECK((long long)p.B * p.H * p.W < (1ll << 31), "swin_fused: token count overflows int32");
+  auto up = [](int v, int a) { return (v + a - 1) / a * a; };
+  // geometry shared with packing.py::fused_block_geometry
+  p.K16 = up(C, 16);
+  p.ones_col = up(3 * C, 8);                 // 8 columns of ones behind q|k|v (softmax denominators via the P V mma)
+  p.NQ = up(p.ones_col + 8, 16);
+  SWN_CHECK(p.NQ <= 256, "swin_fused: NQ too large");
+  p.HC = (4 * C) % 64 == 0 ? 64 : 48;
+  SWN_CHECK((4 * C) % p.HC == 0, "swin_fused: hidden width %d not divisible into chunks", 4 * C);
+  p.nj = (4 * C) / p.HC;
+  p.n_hs = C >= 48 ? 2 : 1;
+  p.RS = p.NQ + 8;
+  if (((p.RS / 8) & 1) == 0) p.RS += 8;       // odd number of 16-byte chunks per row: conflict-free row-per-thread access
+  const int chunks = C / 4;
+  p.RSB = (chunks + ((chunks & 1) ? 0 : 1)) * 16;
+  p.nWy = (p.H + 4) / 5;
+  p.nWx = (p.W + 4) / 5;
+  p.n_windows = (long long)p.B * p.nWy * p.nWx;
+  p.ntiles = (int)((p.n_windows + FB_WIN - 1) / FB_WIN);
+  const int KB = (p.K16 + 63) >> 6;
+  p.w_bytes = (KB * p.NQ + KB * p.K16 + p.nj * KB * p.HC + p.nj * p.K16) * 128;
+  p.nf = 2 * p.NQ + 2 * p.K16 + 4 * C + p.nH * 1024;
+  const int qkv_bytes = 132 * p.RS * 2, hs_bytes = p.n_hs * A_KBLOCK_BYTES;
+  p.u_bytes = up(qkv_bytes > hs_bytes ? qkv_bytes : hs_bytes, 1024);
+  const int HCp = (p.HC + 31) & ~31;
+  const int hacc_cols = (p.nj > 1 ? 2 : 1) * HCp;
+  const int reg0 = up(p.NQ > hacc_cols ? p.NQ : hacc_cols, 32);
+  p.tm_y = reg0;
+  int tc = 32;
+  while (tc < reg0 + p.K16) tc <<= 1;
+  p.tmem_cols = tc;
+  const int threads = C >= 48 ? 512 : 256;
+  const int want = C >= 48 ? 1 : (C >= 24 ? 2 : 3);     // co-resident CTAs per SM hide the serial phase chain
+  size_t smem = 0;
+  auto layout = [&](int n_stage) {
+    p.n_stage = n_stage;
+    p.off_a = up(p.w_bytes, 1024);
+    p.off_u = p.off_a + KB * A_KBLOCK_BYTES;
+    p.off_stage = p.off_u + p.u_bytes;
+    p.off_f = up(p.off_stage + n_stage * 128 * p.RSB, 16);
+    p.off_misc = up(p.off_f + p.nf * 4, 16);
+    smem = (size_t)p.off_misc + 3 * 128 * 4 + (threads / 128) * 128 * 8 + sizeof(FbBars) + 1024;
+  };
+  layout(2);
+  if ((smem + 1024) * want > 233472) layout(1);   // give up the prefetch buffer before giving up a co-resident CTA
+  SWN_CHECK(tc <= 512 && smem <= 232448, "swin_fused: C=%d does not fit (smem %zu, tmem %d)", C, smem, tc);
+  int occ = want;
+  while (occ > 1 && ((smem + 1024) * occ > 233472 || occ * p.tmem_cols > 512)) --occ;
+  long long grid = (long long)num_sms * occ;
+  if (grid > p.ntiles) grid = p.ntiles;
+  auto go = [&](auto kern) -> int {
+    SWN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)grid, threads, smem, stream>>>(p);
+    SWN_CUDA(cudaGetLastError());
+    return 0;
+  };
+  if (threads == 512) {
+    switch (hd) {
+      case 4: return go(swin_fused_kernel<4, 512, 1>);
+      case 8: return go(swin_fused_kernel<8, 512, 1>);
+      case 16: return go(swin_fused_kernel<16, 512, 1>);
+      default: return go(swin_fused_kernel<32, 512, 1>);
+    }
+  }
+  switch (hd) {
+    case 4: return go(swin_fused_kernel<4, 256, 3>);
+    case 8: return go(swin_fused_kernel<8, 256, 2>);
+    case 16: return go(swin_fused_kernel<16, 256, 2>);
+    default: return go(swin_fused_kernel<32, 256, 2>);
+  }
+}
+
+}  // namespace swn

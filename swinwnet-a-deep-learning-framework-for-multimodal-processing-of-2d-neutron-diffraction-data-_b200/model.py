@@ -27,6 +27,7 @@ import torch.nn as nn
 from . import ops, packing
 
 WINDOW = 5
+FUSED_BLOCK = True   # route C <= 64 shift-0 blocks through the single-kernel path (csrc/swin_fused.cu)
 
 
 def _check_infer(x):
@@ -112,6 +113,7 @@ class SwinTransformerBlock(nn.Module):
         hidden = int(dim * mlp_ratio)
         self.mlp = nn.Sequential(nn.Linear(dim, hidden), nn.GELU(), nn.Dropout(drop), nn.Linear(hidden, dim), nn.Dropout(drop))
         self._cache = _PackCache()
+        self._cache_fused = _PackCache()
         if drop or attn_drop or drop_path:
             raise NotImplementedError("swinwnet_b200: dropout/drop_path > 0 is a training feature (not implemented)")
 
@@ -139,6 +141,20 @@ class SwinTransformerBlock(nn.Module):
             return d
         return self._cache.get(src, build)
 
+    def _packed_fused(self):
+        a = self.attn
+        src = [self.norm1.weight, self.norm1.bias, a.qkv.weight, a.qkv.bias, a.relative_position_bias_table,
+               a.proj.weight, a.proj.bias, self.norm2.weight, self.norm2.bias, self.mlp[0].weight, self.mlp[0].bias,
+               self.mlp[3].weight, self.mlp[3].bias]
+
+        def build():
+            if a.qkv.bias is None:
+                raise NotImplementedError("swinwnet_b200: qkv_bias=False is not supported")
+            if self.window_size != WINDOW or int(self.dim * self.mlp_ratio) != 4 * self.dim:
+                raise NotImplementedError("swinwnet_b200: kernels are built for window_size=5, mlp_ratio=4")
+            return packing.pack_fused_block(*src, self.num_heads)
+        return self._cache_fused.get(src, build)
+
     def run(self, x, resolution, out, tmp=None):
         """x [B,L,C] fp32 -> out (may alias x).  `tmp` is a scratch tensor of the same shape: the attention half writes
         x + attn into it and the MLP half reads it, so no kernel ever runs in place (a thread that read-modify-writes its
@@ -146,6 +162,11 @@ class SwinTransformerBlock(nn.Module):
         B, L, C = x.shape
         H, W = resolution
         assert L == H * W, "input feature has wrong size"
+        if FUSED_BLOCK and C <= 48 and self.shift_size == 0 and x.data_ptr() != out.data_ptr():
+            # narrow layers (C = 12 / 24 / 48): the whole block is one tcgen05 kernel (csrc/swin_fused.cu)
+            Wpk, fpk = self._packed_fused()
+            ops.swin_block_fused(x, out, B, H, W, C, self.num_heads, self.norm1.eps, Wpk, fpk, True)
+            return out
         if C in (12, 24) and self.num_heads == 3 and self.window_size == WINDOW and int(C * self.mlp_ratio) == 4 * C \
                 and self.attn.qkv.bias is not None:
             # narrow UpscalingHead layers: the whole block is one fp32 kernel (csrc/small_block.cu)
@@ -189,6 +210,16 @@ class BasicLayer(nn.Module):
             for _ in range(depth)])
 
     def run(self, x, resolution, inplace=False):
+        """returns the layer output; with inplace=True the caller gives up x (it may be overwritten or returned)."""
+        if FUSED_BLOCK and x.shape[-1] <= 48 and all(b.shift_size == 0 for b in self.blocks):
+            # single-kernel blocks never run in place: ping-pong between two buffers
+            spare = None
+            for i, blk in enumerate(self.blocks):
+                dst = spare if spare is not None else torch.empty_like(x)
+                blk.run(x, resolution, dst)
+                spare = x if (inplace or i > 0) else None
+                x = dst
+            return x
         out = x if inplace else torch.empty_like(x)
         tmp = torch.empty_like(x) if (len(self.blocks) and x.shape[-1] not in (12, 24)) else None
         for i, blk in enumerate(self.blocks):
@@ -322,7 +353,7 @@ class SwinDecoder(nn.Module):
             skip = skips[i].float().contiguous()
             assert skip.shape == (B, Hs * Ws, half)
             ops.copy_cols(skip, half, cat, half, C, B * Hs * Ws, half)       # skip -> channels [C/2, C)
-            self.swin_blocks[i].run(cat, (Hs, Ws), inplace=True)
+            cat = self.swin_blocks[i].run(cat, (Hs, Ws), inplace=True)
             lin = self.linears[i]
 
             def build():

@@ -16,7 +16,7 @@ def operand_dtype():
 
 
 LAUNCH_COUNT = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
-_LAUNCHES_PER_CALL = {"swin_block_small": 1, "rowgemm": 1,"mlp": 1, "window_attention": 1, "cross_attention": 1, "patch_embed": 1,
+_LAUNCHES_PER_CALL = {"swin_block_small": 1, "swin_block_fused": 1, "rowgemm": 1,"mlp": 1, "window_attention": 1, "cross_attention": 1, "patch_embed": 1,
                       "seg_head": 2, "recon_head": 1, "copy_cols": 1, "sigmoid_mask": 1, "sigmoid_mask_mm": 2,
                       "normalize": 1}
 
@@ -78,6 +78,14 @@ def swin_block_small(x, out, B, H, W, C, nH, shift, eps, params):
     _lib.check(_lib.load().swn_swin_block_small(_ptr(x), _ptr(out), B, H, W, C, nH, shift, eps, arr, _stream()),
                "swn_swin_block_small")
     _count("swin_block_small")
+
+
+def swin_block_fused(x, out, B, H, W, C, nH, eps, Wpk, fpk, do_mlp=True):
+    """whole shift-0 Swin block (or its attention half) in one tcgen05 kernel, C <= 64; out must not alias x."""
+    _need_cuda(x, out, Wpk, fpk)
+    _lib.check(_lib.load().swn_swin_block_fused(_ptr(x), _ptr(out), B, H, W, C, nH, eps, _ptr(Wpk), _ptr(fpk),
+                                                int(do_mlp), _stream()), "swn_swin_block_fused")
+    _count("swin_block_fused")
 
 
 def window_attention(qkv, out, qkv_bias, table, B, H, W, C, nH, shift=0):

@@ -87,3 +87,91 @@ def pack_mlp(W1: torch.Tensor, W2: torch.Tensor, b2: torch.Tensor, HC: int, TR: 
     b2p = torch.zeros(C16, device=dev)
     b2p[:C] = b2.detach().float()
     return torch.cat(parts).contiguous(), b2p
+
+
+def fused_block_geometry(C: int):
+    """(K16, NQ, HC, nj, ones_col) of csrc/swin_fused.cu::launch_swin_fused for channel width C."""
+    K16 = ceil_to(C, 16)
+    ones_col = ceil_to(3 * C, 8)
+    NQ = ceil_to(ones_col + 8, 16)
+    HC = 64 if (4 * C) % 64 == 0 else 48
+    if (4 * C) % HC:
+        raise ValueError(f"fused block: hidden width {4 * C} not divisible into {HC}-column chunks")
+    return K16, NQ, HC, (4 * C) // HC, ones_col
+
+
+def rel_pos_bias_fragments(table: torch.Tensor, scale: float) -> torch.Tensor:
+    """relative_position_bias_table [81, nH] -> [nH, 2, 4, 32, 4] fp32: for every head the 32x32 (25x25 real) bias
+    matrix laid out as the mma.sync m16n8 accumulator fragments of the attention core (m-tile, n-tile, lane, element):
+    row = mt*16 + lane//4 + (e//2)*8, key = nt*8 + (lane%4)*2 + e%2.  Key columns 25..31 carry -1e30 (masked)."""
+    nH = table.shape[1]
+    dev = table.device
+    t = torch.arange(25, device=dev)
+    R = (t // 5) * 9 + t % 5
+    idx = R[:, None] - R[None, :] + 40                                     # [25, 25] (SwinWNet.py:163-173)
+    full = torch.zeros(nH, 32, 32, device=dev)
+    full[:, :, 25:] = -1e30
+    full[:, :25, :25] = table.detach().float().t()[:, idx] * scale         # [nH, 25, 25]
+    mt, nt, lane, e = torch.meshgrid(torch.arange(2, device=dev), torch.arange(4, device=dev),
+                                     torch.arange(32, device=dev), torch.arange(4, device=dev), indexing="ij")
+    row = mt * 16 + lane // 4 + (e // 2) * 8
+    key = nt * 8 + (lane % 4) * 2 + e % 2
+    return full[:, row, key].contiguous()                                  # [nH, 2, 4, 32, 4]
+
+
+def pack_fused_block(n1w, n1b, Wqkv, bqkv, table, Wproj, bproj, n2w, n2b, W1, b1, W2, b2, num_heads: int):
+    """Parameters of one SwinTransformerBlock (nn.Module layouts) -> (Wpk 16-bit flat, fpk fp32 flat) for
+    csrc/swin_fused.cu.
+
+    Wpk = [Wqkv | Wproj | W1 chunk j | W2 chunk j] as [rows x 64] SWIZZLE_128B k-block images (k-block major inside
+    each matrix).  Algebraic folds done here in fp32 (exact up to the final 16-bit rounding of the operands):
+      * norm1 / norm2 affine into the following linear:  W' = W diag(gamma),  b' = b + W beta  (the kernel only
+        computes (x - mean) * rstd); zero-padded window tokens must still produce the PLAIN qkv bias, which is kept
+        as a second vector;
+      * head_dim^-0.5 * log2(e) into the q rows / q bias and log2(e) into the relative-position bias, so the kernel's
+        softmax is a bare exp2;
+      * rows [ones_col, ones_col+8) of the padded qkv weight are zero with bias 1: the resulting block of ones behind
+        q|k|v turns the softmax denominator into one more column tile of the P V mma.
+    fpk = [bqkv' (NQ) | bqkv plain (NQ) | bproj (K16) | b1' (4C) | b2 (K16) | bias fragments (nH*1024)]."""
+    C = Wqkv.shape[1]
+    K16, NQ, HC, nj, ones_col = fused_block_geometry(C)
+    KB = ceil_to(K16, 64) // 64
+    dev = Wqkv.device
+    LOG2E = 1.4426950408889634
+    qs = (C // num_heads) ** -0.5 * LOG2E
+    f = lambda t: t.detach().float()
+
+    def kmajor(Wm, rows):          # [N, K<=KB*64] -> [KB, rows, 64] swizzled
+        z = torch.zeros(rows, KB * 64, device=dev)
+        z[:Wm.shape[0], :Wm.shape[1]] = Wm
+        return swizzle_tiles(z.view(rows, KB, 64).permute(1, 0, 2).contiguous()).reshape(-1)
+
+    def padv(v, n, fill=0.0):
+        z = torch.full((n,), fill, device=dev)
+        z[:v.numel()] = v.reshape(-1)
+        return z
+
+    Wq, bq_plain = f(Wqkv).clone(), f(bqkv).clone()
+    Wq[:C] *= qs
+    bq_plain[:C] *= qs
+    bq_fold = bq_plain + Wq @ f(n1b)
+    Wq = Wq * f(n1w)[None, :]
+    W1f = f(W1) * f(n2w)[None, :]
+    b1_fold = f(b1) + f(W1) @ f(n2b)
+    W2f = f(W2)
+    parts = [kmajor(Wq, NQ), kmajor(f(Wproj), K16)]
+    for j in range(nj):
+        parts.append(kmajor(W1f[j * HC:(j + 1) * HC], HC))
+    for j in range(nj):
+        z = torch.zeros(K16, 64, device=dev)
+        z[:C, :HC] = W2f[:, j * HC:(j + 1) * HC]
+        parts.append(swizzle_tiles(z).reshape(-1))
+    Wpk = torch.cat(parts).contiguous()
+
+    def qkv_bias(b):
+        z = padv(b, NQ)
+        z[ones_col:ones_col + 8] = 1.0
+        return z
+    fpk = torch.cat([qkv_bias(bq_fold), qkv_bias(bq_plain), padv(f(bproj), K16), padv(b1_fold, 4 * C), padv(f(b2), K16),
+                     rel_pos_bias_fragments(f(table), LOG2E).reshape(-1)]).contiguous()
+    return Wpk, fpk

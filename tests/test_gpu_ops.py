@@ -269,6 +269,43 @@ def test_swin_block_small_fused(C, H, W, shift):
     assert relerr(xd, ref) <= 2e-5
 
 
+def _block_sd(C, nH):
+    shapes = {"norm1.weight": (C,), "norm1.bias": (C,), "attn.qkv.weight": (3 * C, C), "attn.qkv.bias": (3 * C,),
+              "attn.relative_position_bias_table": (81, nH), "attn.proj.weight": (C, C), "attn.proj.bias": (C,),
+              "norm2.weight": (C,), "norm2.bias": (C,), "mlp.0.weight": (4 * C, C), "mlp.0.bias": (4 * C,),
+              "mlp.3.weight": (C, 4 * C), "mlp.3.bias": (C,)}
+    sd = {k: rnd(*s, seed=10 + i) * ((s[-1] ** -0.5) if "weight" in k and len(s) == 2 else 0.2)
+          for i, (k, s) in enumerate(shapes.items())}
+    sd["norm1.weight"] += 1.0
+    sd["norm2.weight"] += 1.0
+    return sd, list(shapes)
+
+
+@pytest.mark.parametrize("C,nH,B,H,W,do_mlp", [
+    (48, 3, 2, 10, 15, True), (48, 3, 1, 13, 9, True), (48, 3, 3, 25, 40, True), (48, 3, 2, 7, 11, False),
+    (24, 3, 2, 10, 15, True), (24, 3, 1, 32, 61, True), (12, 3, 2, 13, 9, True), (12, 3, 1, 40, 65, True),
+    (12, 3, 2, 10, 10, False), (16, 1, 1, 9, 9, True), (32, 2, 1, 12, 23, True)])
+def test_swin_block_fused(C, nH, B, H, W, do_mlp):
+    """tcgen05 whole-block kernel (csrc/swin_fused.cu) against the oracle block: window padding (H, W not multiples of
+    5), ragged last tile (window count not a multiple of 5), several tiles per CTA, attention-only mode."""
+    x = rnd(B, H * W, C, seed=1) * 1.5 + 0.2
+    sd, order = _block_sd(C, nH)
+    if do_mlp:
+        ref = O.swin_block(sd, "", x, (H, W), nH, 0)
+    else:
+        ref = x + O.window_attention(sd, "attn.", O.layer_norm(x, sd["norm1.weight"], sd["norm1.bias"]), (H, W), nH, 0)
+    d = {k: v.to(DEV) for k, v in sd.items()}
+    Wpk, fpk = packing.pack_fused_block(d["norm1.weight"], d["norm1.bias"], d["attn.qkv.weight"], d["attn.qkv.bias"],
+                                        d["attn.relative_position_bias_table"], d["attn.proj.weight"], d["attn.proj.bias"],
+                                        d["norm2.weight"], d["norm2.bias"], d["mlp.0.weight"], d["mlp.0.bias"],
+                                        d["mlp.3.weight"], d["mlp.3.bias"], nH)
+    xd = x.to(DEV)
+    out = torch.full_like(xd, float("nan"))
+    ops.swin_block_fused(xd, out, B, H, W, C, nH, 1e-5, Wpk, fpk, do_mlp)
+    torch.cuda.synchronize()
+    assert relerr(out, ref) <= TOL_BF16 / 4
+
+
 def test_copy_cols():
     src = rnd(37, 48, seed=1).to(DEV)
     dst = torch.zeros(37, 96, device=DEV)
