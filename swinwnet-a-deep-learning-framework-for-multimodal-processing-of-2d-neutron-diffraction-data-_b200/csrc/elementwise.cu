@@ -86,10 +86,12 @@ int launch_patch_embed(const float* x, const float* w, const float* b, const flo
 
 // ---------------------------------------------------------------------------------------------
 // Head tail: tokens (NHWC, CI channels) -> conv3x3(CI->CM, pad 1) -> GELU -> conv1x1(CM->Cout) ->
-// NCHW output cropped to [Hout, Wout].  One thread per pixel; the 3x3 weights sit in shared memory as
-// [tap][ci][cm] and are read as broadcast float4.
+// NCHW output cropped to [Hout, Wout].  fp32 CUDA-core kernel (the heads feed the returned logits / image directly,
+// so they stay in full precision).  A thread owns PX consecutive pixels of a row and all CM mid channels: every
+// broadcast float4 of the [tap][ci][cm] weights in shared memory feeds 4*PX FMAs, which moves the kernel from the
+// shared-memory pipe (one LDS.128 per 4 FMAs in the one-pixel-per-thread form, 3-4x off) to the FMA pipe.
 // ---------------------------------------------------------------------------------------------
-template <int CI, int CM>
+template <int CI, int CM, int PX>
 __global__ void __launch_bounds__(128) conv_head_kernel(const float* __restrict__ tok, const float* __restrict__ w1,
                                                         const float* __restrict__ b1, const float* __restrict__ w2,
                                                         const float* __restrict__ b2, float* __restrict__ out, int B,
@@ -106,49 +108,76 @@ __global__ void __launch_bounds__(128) conv_head_kernel(const float* __restrict_
   for (int i = threadIdx.x; i < Cout * CM; i += blockDim.x) w2_s[i] = w2[i];
   for (int i = threadIdx.x; i < Cout; i += blockDim.x) b2_s[i] = b2[i];
   __syncthreads();
-  const long long total = (long long)B * Hout * Wout;
+  const int groups = (Wout + PX - 1) / PX;                 // pixel groups per output row
+  const long long total = (long long)B * Hout * groups;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total) return;
-  const int b = (int)(t / ((long long)Hout * Wout));
-  const int rem = (int)(t - (long long)b * Hout * Wout);
-  const int y = rem / Wout, x = rem - y * Wout;
-  float acc[CM];
+  const int b = (int)(t / ((long long)Hout * groups));
+  const int rem = (int)(t - (long long)b * Hout * groups);
+  const int y = rem / groups, x0 = (rem - y * groups) * PX;
+  float acc[PX][CM];
 #pragma unroll
-  for (int m = 0; m < CM; ++m) acc[m] = b1_s[m];
+  for (int px = 0; px < PX; ++px)
 #pragma unroll
-  for (int tap = 0; tap < 9; ++tap) {
-    const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
-    if (yy < 0 || yy >= Hh || xx < 0 || xx >= Wh) continue;
-    const float4* src = reinterpret_cast<const float4*>(tok + (((long long)b * Hh + yy) * Wh + xx) * CI);
-    const float* wt = cw_s + tap * CI * CM;
-#pragma unroll 2
+    for (int m = 0; m < CM; ++m) acc[px][m] = b1_s[m];
+#pragma unroll 1
+  for (int dy = 0; dy < 3; ++dy) {
+    const int yy = y + dy - 1;
+    if (yy < 0 || yy >= Hh) continue;
+    const float* rowp = tok + ((long long)b * Hh + yy) * Wh * CI;
+#pragma unroll 1
     for (int c4 = 0; c4 < CI / 4; ++c4) {
-      const float4 v = __ldg(src + c4);
-      const float vv[4] = {v.x, v.y, v.z, v.w};
+      float4 v[PX + 2];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float4* wr = reinterpret_cast<const float4*>(wt + (c4 * 4 + u) * CM);
-#pragma unroll
-        for (int m4 = 0; m4 < CM / 4; ++m4) {
-          const float4 ww = wr[m4];
-          acc[m4 * 4 + 0] = fmaf(vv[u], ww.x, acc[m4 * 4 + 0]);
-          acc[m4 * 4 + 1] = fmaf(vv[u], ww.y, acc[m4 * 4 + 1]);
-          acc[m4 * 4 + 2] = fmaf(vv[u], ww.z, acc[m4 * 4 + 2]);
-          acc[m4 * 4 + 3] = fmaf(vv[u], ww.w, acc[m4 * 4 + 3]);
-        }
+      for (int i = 0; i < PX + 2; ++i) {
+        const int xx = x0 - 1 + i;
+        v[i] = (xx >= 0 && xx < Wh) ? __ldg(reinterpret_cast<const float4*>(rowp + (long long)xx * CI + c4 * 4))
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const float4* wr = reinterpret_cast<const float4*>(cw_s + ((dy * 3 + dx) * CI + c4 * 4 + u) * CM);
+#pragma unroll
+          for (int m4 = 0; m4 < CM / 4; ++m4) {
+            const float4 ww = wr[m4];
+#pragma unroll
+            for (int px = 0; px < PX; ++px) {
+              const float4 vv = v[px + dx];
+              const float a = u == 0 ? vv.x : (u == 1 ? vv.y : (u == 2 ? vv.z : vv.w));
+              acc[px][m4 * 4 + 0] = fmaf(a, ww.x, acc[px][m4 * 4 + 0]);
+              acc[px][m4 * 4 + 1] = fmaf(a, ww.y, acc[px][m4 * 4 + 1]);
+              acc[px][m4 * 4 + 2] = fmaf(a, ww.z, acc[px][m4 * 4 + 2]);
+              acc[px][m4 * 4 + 3] = fmaf(a, ww.w, acc[px][m4 * 4 + 3]);
+            }
+          }
+        }
     }
   }
 #pragma unroll
-  for (int m = 0; m < CM; ++m) {
-    const float a = acc[m];
-    acc[m] = 0.5f * a * (1.0f + erff(a * 0.70710678118654752f));
-  }
-  for (int co = 0; co < Cout; ++co) {
-    float r = b2_s[co];
+  for (int px = 0; px < PX; ++px)
 #pragma unroll
-    for (int m = 0; m < CM; ++m) r = fmaf(acc[m], w2_s[co * CM + m], r);
-    out[(((long long)b * Cout + co) * Hout + y) * Wout + x] = r;
+    for (int m = 0; m < CM; ++m) {
+      const float a = acc[px][m];
+      acc[px][m] = 0.5f * a * (1.0f + erff(a * 0.70710678118654752f));
+    }
+  for (int co = 0; co < Cout; ++co) {
+    float r[PX];
+#pragma unroll
+    for (int px = 0; px < PX; ++px) {
+      r[px] = b2_s[co];
+#pragma unroll
+      for (int m = 0; m < CM; ++m) r[px] = fmaf(acc[px][m], w2_s[co * CM + m], r[px]);
+    }
+    float* dst = out + (((long long)b * Cout + co) * Hout + y) * Wout + x0;
+    if (PX == 4 && (Wout & 3) == 0) {
+      *reinterpret_cast<float4*>(dst) = make_float4(r[0], r[1], r[2], r[3]);
+    } else {
+#pragma unroll
+      for (int px = 0; px < PX; ++px)
+        if (x0 + px < Wout) dst[px] = r[px];
+    }
   }
 }
 
@@ -176,9 +205,10 @@ int launch_seg_head(const float* tok, const float* w1, const float* b1, const fl
                     float* out, int B, int Hq, int Wq, int up, int Hout, int Wout, cudaStream_t st) {
   constexpr int CI = 48, CM = 24;
   const size_t smem = (size_t)(9 * CI * CM + CM + 2 * CM + 2) * sizeof(float);
-  SWN_CUDA(cudaFuncSetAttribute(conv_head_kernel<CI, CM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const long long n_lo = (long long)B * Hq * Wq;
-  conv_head_kernel<CI, CM><<<(unsigned)((n_lo + 127) / 128), 128, smem, st>>>(tok, w1, b1, w2, b2, lowres, B, Hq, Wq, 1, Hq, Wq);
+  constexpr int PX = 4;
+  SWN_CUDA(cudaFuncSetAttribute(conv_head_kernel<CI, CM, PX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long n_lo = (long long)B * Hq * ((Wq + PX - 1) / PX);
+  conv_head_kernel<CI, CM, PX><<<(unsigned)((n_lo + 127) / 128), 128, smem, st>>>(tok, w1, b1, w2, b2, lowres, B, Hq, Wq, 1, Hq, Wq);
   SWN_CUDA(cudaGetLastError());
   const long long n_hi = (long long)B * Hout * Wout;
   bilinear_up_kernel<<<(unsigned)((n_hi + 255) / 256), 256, 0, st>>>(lowres, out, B, Hq, Wq, up, Hout, Wout);
@@ -192,8 +222,9 @@ int launch_recon_head(const float* tok, const float* w1, const float* b1, const 
   SWN_CHECK(Cout >= 1 && Cout <= 2, "recon_head: Cout must be 1 or 2");
   SWN_CHECK(Hout <= Hh && Wout <= Wh, "recon_head: crop larger than source");
   const size_t smem = (size_t)(9 * CI * CM + CM + 2 * CM + 2) * sizeof(float);
-  const long long n = (long long)B * Hout * Wout;
-  conv_head_kernel<CI, CM><<<(unsigned)((n + 127) / 128), 128, smem, st>>>(tok, w1, b1, w2, b2, out, B, Hh, Wh, Cout, Hout, Wout);
+  constexpr int PX = 4;
+  const long long n = (long long)B * Hout * ((Wout + PX - 1) / PX);
+  conv_head_kernel<CI, CM, PX><<<(unsigned)((n + 127) / 128), 128, smem, st>>>(tok, w1, b1, w2, b2, out, B, Hh, Wh, Cout, Hout, Wout);
   SWN_CUDA(cudaGetLastError());
   return 0;
 }

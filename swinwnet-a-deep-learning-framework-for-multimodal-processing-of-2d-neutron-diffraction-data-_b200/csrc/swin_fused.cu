@@ -51,8 +51,26 @@ struct FbBars {
 
 }  // namespace
 
-template <int HD, int NT, int MINB>
+// Geometry of the block for channel width C (mirrored by packing.py::fused_block_geometry and the launcher)
+template <int C_>
+struct FbGeom {
+  static constexpr int C = C_;
+  static constexpr int K16 = (C + 15) / 16 * 16;
+  static constexpr int ONES = (3 * C + 7) / 8 * 8;          // 8 columns of ones behind q|k|v
+  static constexpr int NQ = (ONES + 8 + 15) / 16 * 16;
+  static constexpr int HC = (4 * C) % 64 == 0 ? 64 : 48;    // hidden chunk (columns of one GEMM1 / k-extent of one GEMM2)
+  static constexpr int NJ = (4 * C) / HC;
+  static constexpr int RS0 = NQ + 8;
+  static constexpr int RS = ((RS0 / 8) & 1) ? RS0 : RS0 + 8;  // qkv row stride (16-bit elements): odd number of 16-B chunks
+  static constexpr int RSB = ((C / 4) & 1) ? C * 4 : C * 4 + 16;  // fp32 staging row stride in bytes (odd 16-B chunks)
+  static constexpr int KB = (K16 + 63) / 64;
+  static_assert((4 * C) % HC == 0 && NQ <= 256 && KB == 1, "unsupported channel width");
+};
+
+template <int CC, int NH, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockParams p) {
+  using G = FbGeom<CC>;
+  constexpr int HD = CC / NH;
   constexpr int NP = NT / 128;               // column parts per TMEM lane group
   constexpr int KS = HD >= 16 ? HD / 16 : 1;   // k-steps of S = Q K^T
   constexpr int NTO = HD >= 8 ? HD / 8 : 1;    // 8-wide output column tiles of O = P V
@@ -60,8 +78,14 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
 
-  const int C = p.C, K16 = p.K16, NQ = p.NQ, HC = p.HC, nj = p.nj, nH = p.nH, RS = p.RS, RSB = p.RSB;
-  const int C4 = C >> 2, KB = (K16 + 63) >> 6, ksteps = K16 >> 4;
+  constexpr int C = G::C, K16 = G::K16, NQ = G::NQ, HC = G::HC, nj = G::NJ, nH = NH, RS = G::RS, RSB = G::RSB;
+  constexpr int C4 = C >> 2, KB = G::KB, ksteps = K16 >> 4, ONES = G::ONES;
+  constexpr int HCp = (HC + 31) & ~31;
+  constexpr int NHS = C == 24 ? 1 : nj;                              // hidden-tile buffers (C = 24: smem for 2 CTAs / SM)
+  constexpr int REG0 = ((NQ > nj * HCp ? NQ : nj * HCp) + 31) / 32 * 32;
+  constexpr int TMY = REG0;                                          // TMEM: [0, REG0) qkv / hidden accumulators, then Y
+  constexpr int TMEM_COLS = REG0 + K16 <= 32 ? 32 : REG0 + K16 <= 64 ? 64 : REG0 + K16 <= 128 ? 128 : REG0 + K16 <= 256 ? 256 : 512;
+
   // ---- shared memory carve-up (offsets computed by the launcher) ----
   uint8_t* wq_s = smem;                                   // [KB][NQ x 64]
   uint8_t* wp_s = wq_s + KB * NQ * 128;                   // [KB][K16 x 64]
@@ -97,7 +121,7 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
   for (int i = tid * 16; i < KB * A_KBLOCK_BYTES; i += NT * 16) *reinterpret_cast<uint4*>(a_s + i) = make_uint4(0u, 0u, 0u, 0u);
   for (int i = tid * 16; i < p.u_bytes; i += NT * 16) *reinterpret_cast<uint4*>(u_s + i) = make_uint4(0u, 0u, 0u, 0u);
   for (int i = tid; i < p.nf; i += NT) f_s[i] = p.fpk[i];
-  if (warp == 0) tmem_alloc(&bars->tmem_base, (uint32_t)p.tmem_cols);
+  if (warp == 0) tmem_alloc(&bars->tmem_base, (uint32_t)TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -114,7 +138,6 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
   const uint32_t idesc_c = umma_idesc_bf16(TILE_M, (uint32_t)K16);
   const uint32_t idesc_h = umma_idesc_bf16(TILE_M, (uint32_t)HC);
   const uint64_t a_desc = umma_desc_sw128(smem_u32(a_s));
-  const int HCp = (HC + 31) & ~31;
   const int nWin2 = p.nWy * p.nWx;
 
   auto calc_tok = [&](int tile, int slot) {
@@ -133,7 +156,8 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
     }
   };
   // 16-byte chunk q = tid + i*NT of the [128 x C] tile <-> (row, chunk-in-row), advanced without divisions
-  const int ch_r0 = tid / C4, ch_c0 = tid - ch_r0 * C4, ch_rstep = NT / C4, ch_cstep = NT - ch_rstep * C4;
+  const int ch_r0 = tid / C4, ch_c0 = tid - ch_r0 * C4;
+  constexpr int ch_rstep = NT / C4, ch_cstep = NT - ch_rstep * C4;
   auto issue_loads = [&](int slot, int buf) {
     const uint32_t dst0 = smem_u32(stg + buf * 128 * RSB);
     int r = ch_r0, c4 = ch_c0;
@@ -154,7 +178,10 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
   // rows of invalid tokens are exact zeros)
   auto normalize_rows = [&](const uint8_t* srow, float mean, float rstd, bool valid) {
     const float nm = -mean * rstd;
-    for (int u = part; u < (K16 >> 3); u += NP) {
+    _Pragma("unroll")
+    for (int u_i = 0; u_i < ((K16 >> 3) + NP - 1) / NP; ++u_i) {
+      const int u = part + u_i * NP;
+      if (u >= (K16 >> 3)) break;
       uint32_t pk[4] = {0u, 0u, 0u, 0u};
       if (valid) {
 #pragma unroll
@@ -179,7 +206,7 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
     if (warp == 0) mbar_wait(bar, (phases >> bit) & 1u);
     phases ^= 1u << bit;
   };
-  const float inv_c = 1.0f / (float)C;
+  constexpr float inv_c = 1.0f / (float)C;
   int it = 0;
   const bool prefetch = p.n_stage == 2;
   calc_tok(blockIdx.x, 0);     // grid <= ntiles
@@ -213,7 +240,10 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
     // ---------------- LN1 ----------------
     {
       float s1 = 0.f, s2 = 0.f;
-      for (int c = part * 4; c < C; c += NP * 4) {
+#pragma unroll
+      for (int ci = 0; ci < (C4 + NP - 1) / NP; ++ci) {
+        const int c = (part + ci * NP) * 4;
+        if (c >= C) break;
         const float4 v = *reinterpret_cast<const float4*>(srow + c * 4);
         const float d0 = v.x - x0, d1 = v.y - x0, d2 = v.z - x0, d3 = v.w - x0;
         s1 += (d0 + d1) + (d2 + d3);
@@ -244,7 +274,9 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
       if (elect_one()) {
         const int nchunk = NQ > 256 ? 2 : 1, ncols = NQ / nchunk;
         for (int ch = 0; ch < nchunk; ++ch)
-          for (int k = 0; k < ksteps; ++k) {
+#pragma unroll
+  #pragma unroll
+        for (int k = 0; k < ksteps; ++k) {
             const uint64_t ad = a_desc + (uint64_t)((k >> 2) * (A_KBLOCK_BYTES >> 4) + (k & 3) * 2);
             const uint64_t bd = umma_desc_sw128(smem_u32(wq_s + (k >> 2) * NQ * 128 + ch * ncols * 128)) + (uint64_t)((k & 3) * 2);
             umma_bf16(tmem_base + (uint32_t)(ch * ncols), ad, bd, idesc_q, k != 0 ? 1u : 0u);
@@ -259,7 +291,10 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
     {
       op_t* qrow = reinterpret_cast<op_t*>(u_s) + row * RS;
       float v[16];
-      for (int cu = part; cu < (NQ >> 4); cu += NP) {
+      _Pragma("unroll")
+      for (int cu_i = 0; cu_i < ((NQ >> 4) + NP - 1) / NP; ++cu_i) {
+        const int cu = part + cu_i * NP;
+        if (cu >= (NQ >> 4)) break;
         tmem_ld16(lane_addr + (uint32_t)(cu * 16), v);
         tmem_ld_wait();
         const float* bb = (tokr >= 0 ? bqkv : bqkv_pad) + cu * 16;
@@ -352,7 +387,7 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
           fb_mma(o[0][n], pa[0][ks], b0, b1);
           fb_mma(o[1][n], pa[1][ks], b0, b1);
         }
-        fb_ldsm_x2_trans(b0, b1, vrow + p.ones_col * 2);
+        fb_ldsm_x2_trans(b0, b1, vrow + ONES * 2);
         fb_mma(od[0], pa[0][ks], b0, b1);
         fb_mma(od[1], pa[1][ks], b0, b1);
       }
@@ -386,10 +421,11 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
     if (warp == 0) {
       tc_fence_after();
       if (elect_one()) {
+#pragma unroll
         for (int k = 0; k < ksteps; ++k) {
           const uint64_t ad = a_desc + (uint64_t)((k >> 2) * (A_KBLOCK_BYTES >> 4) + (k & 3) * 2);
           const uint64_t bd = umma_desc_sw128(smem_u32(wp_s + (k >> 2) * K16 * 128)) + (uint64_t)((k & 3) * 2);
-          umma_bf16(tmem_base + (uint32_t)p.tm_y, ad, bd, idesc_c, k != 0 ? 1u : 0u);
+          umma_bf16(tmem_base + (uint32_t)TMY, ad, bd, idesc_c, k != 0 ? 1u : 0u);
         }
         umma_commit(&bars->mma);
       }
@@ -402,8 +438,11 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
       // x1 = x + proj + bias, written back to the staging row; partial LN2 moments on the fly
       float s1 = 0.f, s2 = 0.f;
       float v[16];
-      for (int cu = part; cu < (K16 >> 4); cu += NP) {
-        tmem_ld16(lane_addr + (uint32_t)(p.tm_y + cu * 16), v);
+      _Pragma("unroll")
+      for (int cu_i = 0; cu_i < ((K16 >> 4) + NP - 1) / NP; ++cu_i) {
+        const int cu = part + cu_i * NP;
+        if (cu >= (K16 >> 4)) break;
+        tmem_ld16(lane_addr + (uint32_t)(TMY + cu * 16), v);
         tmem_ld_wait();
 #pragma unroll
         for (int j4 = 0; j4 < 16; j4 += 4) {
@@ -445,36 +484,89 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
       fence_proxy_async();
       __syncthreads();
 
-      // ---------------- MLP: hidden chunks of HC columns; GEMM1(j+1) is in flight during the GELU epilogue of j --------
-      auto issue_g1 = [&](int j) {
-        if (warp == 0) {
-          tc_fence_after();
-          if (elect_one()) {
+      // ---------------- MLP: all GEMM1 chunks are issued at once (TMEM columns [j*HCp, j*HCp + HC)); the GELU epilogue
+      // of chunk j fills hidden tile j and GEMM2(j) accumulates Y behind it, so only two MMA round trips are exposed ----
+      if (warp == 0) {
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int j = 0; j < nj; ++j)
+#pragma unroll
             for (int k = 0; k < ksteps; ++k) {
               const uint64_t ad = a_desc + (uint64_t)((k >> 2) * (A_KBLOCK_BYTES >> 4) + (k & 3) * 2);
               const uint64_t bd = umma_desc_sw128(smem_u32(w1_s + (j * KB + (k >> 2)) * HC * 128)) + (uint64_t)((k & 3) * 2);
-              umma_bf16(tmem_base + (uint32_t)((j & 1) * HCp), ad, bd, idesc_h, k != 0 ? 1u : 0u);
+              umma_bf16(tmem_base + (uint32_t)(j * HCp), ad, bd, idesc_h, k != 0 ? 1u : 0u);
             }
-            umma_commit(&bars->g1[j & 1]);
+          umma_commit(&bars->g1[0]);
+        }
+        __syncwarp();
+      }
+      wait_bar(&bars->g1[0], 1);
+      __syncthreads();
+      tc_fence_after();
+      if constexpr (NHS == nj && nj > 1) {
+        // one hidden tile per chunk: all GELU epilogues back to back (TMEM loads of every chunk in flight before the
+        // first GELU), one barrier, then all GEMM2 chunks
+        constexpr int UPT = ((HC >> 4) + NP - 1) / NP;     // 16-column units per thread and chunk
+        float v[nj * UPT][16];
+#pragma unroll
+        for (int j = 0; j < nj; ++j)
+#pragma unroll
+          for (int ui = 0; ui < UPT; ++ui) {
+            const int cu = part + ui * NP;
+            if (cu < (HC >> 4)) tmem_ld16(lane_addr + (uint32_t)(j * HCp + cu * 16), v[j * UPT + ui]);
+          }
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < nj; ++j)
+#pragma unroll
+          for (int ui = 0; ui < UPT; ++ui) {
+            const int cu = part + ui * NP;
+            if (cu < (HC >> 4)) {
+              const float* bj = b1 + j * HC + cu * 16;
+              const float* vv = v[j * UPT + ui];
+              uint32_t pk[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) pk[i] = pack_op(gelu_fast(vv[2 * i] + bj[2 * i]), gelu_fast(vv[2 * i + 1] + bj[2 * i + 1]));
+              uint8_t* hs = u_s + j * A_KBLOCK_BYTES;
+              *reinterpret_cast<uint4*>(hs + sw128_offset(row, cu * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              *reinterpret_cast<uint4*>(hs + sw128_offset(row, cu * 16 + 8)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
+          }
+        tc_fence_before();
+        fence_proxy_async();
+        __syncthreads();
+        if (warp == 0) {
+          tc_fence_after();
+          if (elect_one()) {
+#pragma unroll
+            for (int j = 0; j < nj; ++j) {
+              const uint64_t hd0 = umma_desc_sw128(smem_u32(u_s + j * A_KBLOCK_BYTES));
+              const uint64_t bd0 = umma_desc_sw128(smem_u32(w2_s + j * K16 * 128));
+#pragma unroll
+              for (int k = 0; k < (HC >> 4); ++k)
+                umma_bf16(tmem_base + (uint32_t)TMY, hd0 + (uint64_t)(2 * k), bd0 + (uint64_t)(2 * k), idesc_c, (j | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&bars->g2[0]);
           }
           __syncwarp();
         }
-      };
-      issue_g1(0);
-      int last_hb = 0;
+      } else {
+#pragma unroll
       for (int j = 0; j < nj; ++j) {
-        if (j + 1 < nj) issue_g1(j + 1);
-        const int hb = p.n_hs == 2 ? (j & 1) : 0;
-        wait_bar(&bars->g1[j & 1], 1 + (j & 1));
-        if (j >= p.n_hs) wait_bar(&bars->g2[hb], 3 + hb);   // the hidden tile buffer is free once GEMM2(j - n_hs) retired
-        __syncthreads();
-        tc_fence_after();
-        uint8_t* hs = u_s + hb * A_KBLOCK_BYTES;
+        if (j > 0) {   // single hidden tile: wait until GEMM2(j-1) has consumed it
+          wait_bar(&bars->g2[0], 3);
+          __syncthreads();
+        }
+        uint8_t* hs = u_s;
         {
           float v[16];
           const float* bj = b1 + j * HC;
-          for (int cu = part; cu < (HC >> 4); cu += NP) {
-            tmem_ld16(lane_addr + (uint32_t)((j & 1) * HCp + cu * 16), v);
+          _Pragma("unroll")
+          for (int cu_i = 0; cu_i < ((HC >> 4) + NP - 1) / NP; ++cu_i) {
+            const int cu = part + cu_i * NP;
+            if (cu >= (HC >> 4)) break;
+            tmem_ld16(lane_addr + (uint32_t)(j * HCp + cu * 16), v);
             tmem_ld_wait();
             uint32_t pk[8];
 #pragma unroll
@@ -492,29 +584,25 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
           if (elect_one()) {
             const uint64_t hd0 = umma_desc_sw128(smem_u32(hs));
             const uint64_t bd0 = umma_desc_sw128(smem_u32(w2_s + j * K16 * 128));
+#pragma unroll
             for (int k = 0; k < (HC >> 4); ++k)
-              umma_bf16(tmem_base + (uint32_t)p.tm_y, hd0 + (uint64_t)(2 * k), bd0 + (uint64_t)(2 * k), idesc_c, (j | k) != 0 ? 1u : 0u);
-            umma_commit(&bars->g2[hb]);
+              umma_bf16(tmem_base + (uint32_t)TMY, hd0 + (uint64_t)(2 * k), bd0 + (uint64_t)(2 * k), idesc_c, (j | k) != 0 ? 1u : 0u);
+            umma_commit(&bars->g2[0]);
           }
           __syncwarp();
         }
-        last_hb = hb;
       }
-      // drain the GEMM2 commits that nobody waited for yet (every phase of every barrier is observed exactly once)
-      {
-        const int pending0 = p.n_hs == 2 ? min(nj, 2) : 1;
-        if (pending0 == 2) {
-          const int other = last_hb ^ 1;
-          wait_bar(&bars->g2[other], 3 + other);
-        }
-        wait_bar(&bars->g2[last_hb], 3 + last_hb);
       }
+      wait_bar(&bars->g2[0], 3);
       __syncthreads();
       tc_fence_after();
       {
         float v[16];
-        for (int cu = part; cu < (K16 >> 4); cu += NP) {
-          tmem_ld16(lane_addr + (uint32_t)(p.tm_y + cu * 16), v);
+        _Pragma("unroll")
+        for (int cu_i = 0; cu_i < ((K16 >> 4) + NP - 1) / NP; ++cu_i) {
+          const int cu = part + cu_i * NP;
+          if (cu >= (K16 >> 4)) break;
+          tmem_ld16(lane_addr + (uint32_t)(TMY + cu * 16), v);
           tmem_ld_wait();
 #pragma unroll
           for (int j4 = 0; j4 < 16; j4 += 4) {
@@ -553,7 +641,7 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    tmem_dealloc(tmem_base, (uint32_t)TMEM_COLS);
   }
 }
 
@@ -562,7 +650,7 @@ int launch_swin_fused(FusedBlockParams p, int num_sms, cudaStream_t stream) {
   SWN_CHECK(p.B > 0 && p.H > 0 && p.W > 0 && C >= 4 && C % 4 == 0 && C <= 48 && p.nH > 0 && C % p.nH == 0,
             "swin_fused: unsupported C=%d nH=%d", C, p.nH);
   const int hd = C / p.nH;
-  SWN_CHECK(hd == 4 || hd == 8 || hd == 16 || hd == 32, "swin_fused: unsupported head_dim %d", hd);
+  (void)hd;
   SWN_CHECK((long long)p.B * p.H * p.W < (1ll << 31), "swin_fused: token count overflows int32");
   auto up = [](int v, int a) { return (v + a - 1) / a * a; };
   // geometry shared with packing.py::fused_block_geometry
@@ -573,7 +661,7 @@ int launch_swin_fused(FusedBlockParams p, int num_sms, cudaStream_t stream) {
   p.HC = (4 * C) % 64 == 0 ? 64 : 48;
   SWN_CHECK((4 * C) % p.HC == 0, "swin_fused: hidden width %d not divisible into chunks", 4 * C);
   p.nj = (4 * C) / p.HC;
-  p.n_hs = C >= 48 ? 2 : 1;
+  p.n_hs = C == 24 ? 1 : p.nj;
   p.RS = p.NQ + 8;
   if (((p.RS / 8) & 1) == 0) p.RS += 8;       // odd number of 16-byte chunks per row: conflict-free row-per-thread access
   const int chunks = C / 4;
@@ -588,7 +676,7 @@ int launch_swin_fused(FusedBlockParams p, int num_sms, cudaStream_t stream) {
   const int qkv_bytes = 132 * p.RS * 2, hs_bytes = p.n_hs * A_KBLOCK_BYTES;
   p.u_bytes = up(qkv_bytes > hs_bytes ? qkv_bytes : hs_bytes, 1024);
   const int HCp = (p.HC + 31) & ~31;
-  const int hacc_cols = (p.nj > 1 ? 2 : 1) * HCp;
+  const int hacc_cols = p.nj * HCp;
   const int reg0 = up(p.NQ > hacc_cols ? p.NQ : hacc_cols, 32);
   p.tm_y = reg0;
   int tc = 32;
@@ -619,20 +707,12 @@ int launch_swin_fused(FusedBlockParams p, int num_sms, cudaStream_t stream) {
     SWN_CUDA(cudaGetLastError());
     return 0;
   };
-  if (threads == 512) {
-    switch (hd) {
-      case 4: return go(swin_fused_kernel<4, 512, 1>);
-      case 8: return go(swin_fused_kernel<8, 512, 1>);
-      case 16: return go(swin_fused_kernel<16, 512, 1>);
-      default: return go(swin_fused_kernel<32, 512, 1>);
-    }
-  }
-  switch (hd) {
-    case 4: return go(swin_fused_kernel<4, 256, 3>);
-    case 8: return go(swin_fused_kernel<8, 256, 2>);
-    case 16: return go(swin_fused_kernel<16, 256, 2>);
-    default: return go(swin_fused_kernel<32, 256, 2>);
-  }
+  if (C == 12 && p.nH == 3) return go(swin_fused_kernel<12, 3, 256, 3>);
+  if (C == 24 && p.nH == 3) return go(swin_fused_kernel<24, 3, 256, 2>);
+  if (C == 48 && p.nH == 3) return go(swin_fused_kernel<48, 3, 512, 1>);
+  if (C == 48 && p.nH == 6) return go(swin_fused_kernel<48, 6, 512, 1>);
+  SWN_CHECK(false, "swin_fused: no kernel instance for C=%d nH=%d (built: 12/3, 24/3, 48/3, 48/6)", C, p.nH);
+  return 1;
 }
 
 }  // namespace swn

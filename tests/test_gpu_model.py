@@ -204,7 +204,22 @@ def test_acceptance_gates_surrogate_checkpoint(surrogate):
     assert abs(p_c - p_o) <= 0.05
     m_c = DM.physical_metrics(c[3].numpy(), o[1].numpy())
     m_o = DM.physical_metrics(o[3].numpy(), o[1].numpy())
+    # Conditioning of the gauge itself: the metric goes through scipy.find_peaks thresholds and integer peak windows
+    # (Diffraction_metrics.py:96-144), so on some samples it is bistable — the ORACLE's own value jumps by orders of
+    # magnitude under a 1e-3 (max-norm) random perturbation of its own output, twenty times below the 2e-2 tolerance of
+    # the images (measured: sample 3 of seed 41 flips between 2.264 and 161.36).  Such samples cannot gauge a 1 %
+    # agreement; they are detected here with the oracle alone (never with the CUDA result) and left out of the mean.
+    den_o = o[3]
+    stable = np.ones(B, dtype=bool)
+    for seed in range(8):
+        g = torch.Generator().manual_seed(1000 + seed)
+        noisy = den_o + torch.randn(den_o.shape, generator=g) * den_o.abs().max() * 1e-3
+        m_n = DM.physical_metrics(noisy.numpy(), o[1].numpy())
+        for k in ("Integral Intensity", "Peak Intensity"):
+            stable &= np.abs(np.asarray(m_n[k]) - np.asarray(m_o[k])) <= 0.005 * np.abs(np.asarray(m_o[k])) + 1e-9
+    print("well-conditioned samples for the physics gauge:", stable.tolist())
+    assert stable.sum() >= 2, "physics gauge is ill-conditioned on almost every sample of this batch"
     for k in ("Integral Intensity", "Peak Intensity"):
-        a, b = float(np.mean(m_c[k])), float(np.mean(m_o[k]))
+        a, b = float(np.mean(np.asarray(m_c[k])[stable])), float(np.mean(np.asarray(m_o[k])[stable]))
         print(k, "cuda / oracle:", a, b, "per-sample", m_c[k], m_o[k])
         assert b > 0 and abs(a - b) <= 0.01 * abs(b), (k, a, b)

@@ -228,6 +228,11 @@ def test_recon_head_and_glue():
     ops.recon_head(x.to(DEV), w1.to(DEV), b1.to(DEV), w2.to(DEV), b2.to(DEV), out, B, H, W, 2, 10, 18)
     torch.cuda.synchronize()
     assert relerr(out, ref) <= TOL_F32
+    full = (h @ w2.view(2, 12).t() + b2).permute(0, 3, 1, 2)            # uncropped, row length a multiple of 4
+    out4 = torch.empty(B, 2, H, W, device=DEV)
+    ops.recon_head(x.to(DEV), w1.to(DEV), b1.to(DEV), w2.to(DEV), b2.to(DEV), out4, B, H, W, 2, H, W)
+    torch.cuda.synchronize()
+    assert relerr(out4, full) <= TOL_F32
     # glue: ensure_2ch + sigmoid mask + minmax + normalize / denormalize round trip
     img = rnd(B, 1, H, W, seed=6).abs() * 100 + 5
     seg = rnd(B, 1, H, W, seed=7)
@@ -284,7 +289,8 @@ def _block_sd(C, nH):
 @pytest.mark.parametrize("C,nH,B,H,W,do_mlp", [
     (48, 3, 2, 10, 15, True), (48, 3, 1, 13, 9, True), (48, 3, 3, 25, 40, True), (48, 3, 2, 7, 11, False),
     (24, 3, 2, 10, 15, True), (24, 3, 1, 32, 61, True), (12, 3, 2, 13, 9, True), (12, 3, 1, 40, 65, True),
-    (12, 3, 2, 10, 10, False), (16, 1, 1, 9, 9, True), (32, 2, 1, 12, 23, True)])
+    (12, 3, 2, 10, 10, False), (48, 6, 1, 12, 23, True),
+    (48, 3, 2, 100, 101, True), (24, 3, 1, 180, 175, True), (12, 3, 1, 240, 245, True)])   # several tiles per persistent CTA
 def test_swin_block_fused(C, nH, B, H, W, do_mlp):
     """tcgen05 whole-block kernel (csrc/swin_fused.cu) against the oracle block: window padding (H, W not multiples of
     5), ragged last tile (window count not a multiple of 5), several tiles per CTA, attention-only mode."""
