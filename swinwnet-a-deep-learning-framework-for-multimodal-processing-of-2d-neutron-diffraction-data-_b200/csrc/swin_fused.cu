@@ -67,13 +67,123 @@ struct FbGeom {
   static_assert((4 * C) % HC == 0 && NQ <= 256 && KB == 1, "unsupported channel width");
 };
 
+// One (window, head) pair of the attention core, executed by one warp: S = Q K^T (+ bias image) on mma.sync, softmax,
+// O = P V, normalised O -> the 16-bit A tile of the proj GEMM.  qkv rows live in `u_s` as [row][RS] 16-bit with
+// q | k | v | ones at columns 0 | C | 2C | ONES; the window's tokens are rows wl*25 .. wl*25+24.
+template <int HD, int C, int RS, int ONES>
+__device__ __forceinline__ void fb_attention_pair(const uint8_t* u_s, uint8_t* a_s, const float4* biasfrag, int wl, int h,
+                                                  int lane) {
+  constexpr int KS = HD >= 16 ? HD / 16 : 1;   // k-steps of S = Q K^T
+  constexpr int NTO = HD >= 8 ? HD / 8 : 1;    // 8-wide output column tiles of O = P V
+  const int g = lane >> 2, t4 = lane & 3;
+  const op_t* base = reinterpret_cast<const op_t*>(u_s) + wl * FB_TOK * RS;
+  const int qoff = h * HD, koff = C + h * HD, voff = 2 * C + h * HD;
+  // accumulators start from the relative-position bias image of this head (log2 domain, -1e30 on the key columns
+  // 25..31 that belong to the next window / padding): the softmax argument comes straight out of the mma
+  float s[2][4][4];
+  {
+    const float4* bf = biasfrag + h * 256 + lane;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const float4 b4 = bf[(mt * 4 + nt) * 32];
+        s[mt][nt][0] = b4.x; s[mt][nt][1] = b4.y; s[mt][nt][2] = b4.z; s[mt][nt][3] = b4.w;
+      }
+  }
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+    const int col = ks * 16 + t4 * 2;
+    uint32_t a[2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const op_t* qr = base + (mt * 16 + g) * RS + qoff + col;
+      a[mt][0] = col < HD ? *reinterpret_cast<const uint32_t*>(qr) : 0u;
+      a[mt][1] = col < HD ? *reinterpret_cast<const uint32_t*>(qr + 8 * RS) : 0u;
+      a[mt][2] = col + 8 < HD ? *reinterpret_cast<const uint32_t*>(qr + 8) : 0u;
+      a[mt][3] = col + 8 < HD ? *reinterpret_cast<const uint32_t*>(qr + 8 * RS + 8) : 0u;
+    }
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const op_t* kr = base + (nt * 8 + g) * RS + koff + col;
+      const uint32_t b0 = col < HD ? *reinterpret_cast<const uint32_t*>(kr) : 0u;
+      const uint32_t b1 = col + 8 < HD ? *reinterpret_cast<const uint32_t*>(kr + 8) : 0u;
+      fb_mma(s[0][nt], a[0], b0, b1);
+      fb_mma(s[1][nt], a[1], b0, b1);
+    }
+  }
+  // P = 2^(s - rowmax) as 16-bit A fragments; the row sums come out of the P V mma through the ones block of qkv_s
+  uint32_t pa[2][2][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    float m0 = fmaxf(fmaxf(s[mt][0][0], s[mt][0][1]), fmaxf(s[mt][1][0], s[mt][1][1]));
+    m0 = fmaxf(m0, fmaxf(fmaxf(s[mt][2][0], s[mt][2][1]), fmaxf(s[mt][3][0], s[mt][3][1])));
+    float m1 = fmaxf(fmaxf(s[mt][0][2], s[mt][0][3]), fmaxf(s[mt][1][2], s[mt][1][3]));
+    m1 = fmaxf(m1, fmaxf(fmaxf(s[mt][2][2], s[mt][2][3]), fmaxf(s[mt][3][2], s[mt][3][3])));
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      pa[mt][ks][0] = fb_exp2_pack(s[mt][2 * ks][0], s[mt][2 * ks][1], m0);
+      pa[mt][ks][1] = fb_exp2_pack(s[mt][2 * ks][2], s[mt][2 * ks][3], m1);
+      pa[mt][ks][2] = fb_exp2_pack(s[mt][2 * ks + 1][0], s[mt][2 * ks + 1][1], m0);
+      pa[mt][ks][3] = fb_exp2_pack(s[mt][2 * ks + 1][2], s[mt][2 * ks + 1][3], m1);
+    }
+  }
+  // O = P V  (+ one extra 8-column tile of ones: its accumulator is the softmax denominator of the row)
+  const int vcol0 = voff & ~7;
+  float o[2][NTO][4], od[2][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    od[mt][0] = od[mt][1] = od[mt][2] = od[mt][3] = 0.f;
+#pragma unroll
+    for (int n = 0; n < NTO; ++n) o[mt][n][0] = o[mt][n][1] = o[mt][n][2] = o[mt][n][3] = 0.f;
+  }
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    const uint32_t vrow = smem_u32(base + (ks * 16 + (lane & 15)) * RS);
+    uint32_t b0, b1;
+#pragma unroll
+    for (int n = 0; n < NTO; ++n) {
+      fb_ldsm_x2_trans(b0, b1, vrow + (vcol0 + n * 8) * 2);
+      fb_mma(o[0][n], pa[0][ks], b0, b1);
+      fb_mma(o[1][n], pa[1][ks], b0, b1);
+    }
+    fb_ldsm_x2_trans(b0, b1, vrow + ONES * 2);
+    fb_mma(od[0], pa[0][ks], b0, b1);
+    fb_mma(od[1], pa[1][ks], b0, b1);
+  }
+  float inv[2][2];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    inv[mt][0] = rcp_approx(od[mt][0]);
+    inv[mt][1] = rcp_approx(od[mt][2]);
+  }
+  // normalised O -> A tile (16-bit, swizzled), rows wl*25 + i, columns h*HD + d
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int n = 0; n < NTO; ++n) {
+      const int dcol = n * 8 + t4 * 2 - (voff - vcol0);
+      if (dcol >= 0 && dcol < HD) {
+        const int k = qoff + dcol;
+        const int i0 = mt * 16 + g, i1 = i0 + 8;
+        uint8_t* kb = a_s + (k >> 6) * A_KBLOCK_BYTES;
+        if (i0 < FB_TOK)
+          *reinterpret_cast<uint32_t*>(kb + sw128_offset(wl * FB_TOK + i0, k & 63)) = pack_op(o[mt][n][0] * inv[mt][0], o[mt][n][1] * inv[mt][0]);
+        if (i1 < FB_TOK)
+          *reinterpret_cast<uint32_t*>(kb + sw128_offset(wl * FB_TOK + i1, k & 63)) = pack_op(o[mt][n][2] * inv[mt][1], o[mt][n][3] * inv[mt][1]);
+      }
+    }
+}
+
 template <int CC, int NH, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockParams p) {
   using G = FbGeom<CC>;
   constexpr int HD = CC / NH;
   constexpr int NP = NT / 128;               // column parts per TMEM lane group
-  constexpr int KS = HD >= 16 ? HD / 16 : 1;   // k-steps of S = Q K^T
-  constexpr int NTO = HD >= 8 ? HD / 8 : 1;    // 8-wide output column tiles of O = P V
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -107,7 +217,6 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row = tid & 127, part = tid >> 7;
-  const int g = lane >> 2, t4 = lane & 3;
 
   if (tid == 0) {
     mbar_init(&bars->w, 1);
@@ -312,107 +421,7 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
     for (int pr = warp; pr < FB_WIN * nH; pr += NT / 32) {
       const int wl = pr / nH, h = pr - wl * nH;
       if ((long long)tile * FB_WIN + wl >= p.n_windows) continue;
-      const op_t* base = reinterpret_cast<const op_t*>(u_s) + wl * FB_TOK * RS;
-      const int qoff = h * HD, koff = C + h * HD, voff = 2 * C + h * HD;
-      // accumulators start from the relative-position bias image of this head (log2 domain, -1e30 on the key columns
-      // 25..31 that belong to the next window / padding): the softmax argument comes straight out of the mma
-      float s[2][4][4];
-      {
-        const float4* bf = biasfrag + h * 256 + lane;
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-          for (int nt = 0; nt < 4; ++nt) {
-            const float4 b4 = bf[(mt * 4 + nt) * 32];
-            s[mt][nt][0] = b4.x; s[mt][nt][1] = b4.y; s[mt][nt][2] = b4.z; s[mt][nt][3] = b4.w;
-          }
-      }
-#pragma unroll
-      for (int ks = 0; ks < KS; ++ks) {
-        const int col = ks * 16 + t4 * 2;
-        uint32_t a[2][4];
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-          const op_t* qr = base + (mt * 16 + g) * RS + qoff + col;
-          a[mt][0] = col < HD ? *reinterpret_cast<const uint32_t*>(qr) : 0u;
-          a[mt][1] = col < HD ? *reinterpret_cast<const uint32_t*>(qr + 8 * RS) : 0u;
-          a[mt][2] = col + 8 < HD ? *reinterpret_cast<const uint32_t*>(qr + 8) : 0u;
-          a[mt][3] = col + 8 < HD ? *reinterpret_cast<const uint32_t*>(qr + 8 * RS + 8) : 0u;
-        }
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-          const op_t* kr = base + (nt * 8 + g) * RS + koff + col;
-          const uint32_t b0 = col < HD ? *reinterpret_cast<const uint32_t*>(kr) : 0u;
-          const uint32_t b1 = col + 8 < HD ? *reinterpret_cast<const uint32_t*>(kr + 8) : 0u;
-          fb_mma(s[0][nt], a[0], b0, b1);
-          fb_mma(s[1][nt], a[1], b0, b1);
-        }
-      }
-      // P = 2^(s - rowmax) as 16-bit A fragments; the row sums come out of the P V mma through the ones block of qkv_s
-      uint32_t pa[2][2][4];
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
-        float m0 = fmaxf(fmaxf(s[mt][0][0], s[mt][0][1]), fmaxf(s[mt][1][0], s[mt][1][1]));
-        m0 = fmaxf(m0, fmaxf(fmaxf(s[mt][2][0], s[mt][2][1]), fmaxf(s[mt][3][0], s[mt][3][1])));
-        float m1 = fmaxf(fmaxf(s[mt][0][2], s[mt][0][3]), fmaxf(s[mt][1][2], s[mt][1][3]));
-        m1 = fmaxf(m1, fmaxf(fmaxf(s[mt][2][2], s[mt][2][3]), fmaxf(s[mt][3][2], s[mt][3][3])));
-        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
-        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
-        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
-        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-          pa[mt][ks][0] = fb_exp2_pack(s[mt][2 * ks][0], s[mt][2 * ks][1], m0);
-          pa[mt][ks][1] = fb_exp2_pack(s[mt][2 * ks][2], s[mt][2 * ks][3], m1);
-          pa[mt][ks][2] = fb_exp2_pack(s[mt][2 * ks + 1][0], s[mt][2 * ks + 1][1], m0);
-          pa[mt][ks][3] = fb_exp2_pack(s[mt][2 * ks + 1][2], s[mt][2 * ks + 1][3], m1);
-        }
-      }
-      // O = P V  (+ one extra 8-column tile of ones: its accumulator is the softmax denominator of the row)
-      const int vcol0 = voff & ~7;
-      float o[2][NTO][4], od[2][4];
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
-        od[mt][0] = od[mt][1] = od[mt][2] = od[mt][3] = 0.f;
-#pragma unroll
-        for (int n = 0; n < NTO; ++n) o[mt][n][0] = o[mt][n][1] = o[mt][n][2] = o[mt][n][3] = 0.f;
-      }
-#pragma unroll
-      for (int ks = 0; ks < 2; ++ks) {
-        const uint32_t vrow = smem_u32(base + (ks * 16 + (lane & 15)) * RS);
-        uint32_t b0, b1;
-#pragma unroll
-        for (int n = 0; n < NTO; ++n) {
-          fb_ldsm_x2_trans(b0, b1, vrow + (vcol0 + n * 8) * 2);
-          fb_mma(o[0][n], pa[0][ks], b0, b1);
-          fb_mma(o[1][n], pa[1][ks], b0, b1);
-        }
-        fb_ldsm_x2_trans(b0, b1, vrow + ONES * 2);
-        fb_mma(od[0], pa[0][ks], b0, b1);
-        fb_mma(od[1], pa[1][ks], b0, b1);
-      }
-      float inv[2][2];
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
-        inv[mt][0] = rcp_approx(od[mt][0]);
-        inv[mt][1] = rcp_approx(od[mt][2]);
-      }
-      // normalised O -> A tile (16-bit, swizzled), rows wl*25 + i, columns h*HD + d
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int n = 0; n < NTO; ++n) {
-          const int dcol = n * 8 + t4 * 2 - (voff - vcol0);
-          if (dcol >= 0 && dcol < HD) {
-            const int k = qoff + dcol;
-            const int i0 = mt * 16 + g, i1 = i0 + 8;
-            uint8_t* kb = a_s + (k >> 6) * A_KBLOCK_BYTES;
-            if (i0 < FB_TOK)
-              *reinterpret_cast<uint32_t*>(kb + sw128_offset(wl * FB_TOK + i0, k & 63)) = pack_op(o[mt][n][0] * inv[mt][0], o[mt][n][1] * inv[mt][0]);
-            if (i1 < FB_TOK)
-              *reinterpret_cast<uint32_t*>(kb + sw128_offset(wl * FB_TOK + i1, k & 63)) = pack_op(o[mt][n][2] * inv[mt][1], o[mt][n][3] * inv[mt][1]);
-          }
-        }
+      fb_attention_pair<HD, C, RS, ONES>(u_s, a_s, biasfrag, wl, h, lane);
     }
     fence_proxy_async();
     __syncthreads();
@@ -645,8 +654,347 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
   }
 }
 
+// =================================================================================================================
+// Streamed-weight variant for C = 96 (heads 3 or 6): the attention half  out = x + proj(W-MSA(LN1(x)))  only (the MLP
+// half runs in mlp_persist.cu).  At this width the weights (100 KB) and the q|k|v rows (82 KB) do not fit next to each
+// other, so the six weight tiles of a token tile [Wqkv rows 0-159 | 160-303] x [k-block 0 | 1], Wproj x [kb 0 | 1]
+// stream through a 4-slot ring.  The thread that issues the MMAs also issues the bulk copies, at the two points of
+// the tile where program order proves the slots free (after the qkv MMAs and after the proj MMAs have retired), so
+// the ring needs no "empty" barriers and the next tile's qkv weights are in flight during the attention phase.
+// The q|k|v buffer doubles as the fp32 staging buffer of the token rows: it is free from the end of the attention
+// phase of tile i to the qkv epilogue of tile i+1, which is when the rows of tile i+1 are gathered into it with
+// cp.async (behind the proj MMA and epilogue of tile i).  The residual of tile i is re-read from global memory (L2
+// hit) into registers before the proj MMA is waited for, and the result is written straight from the epilogue
+// registers.  The qkv bias rides in the GEMM: A carries two indicator columns (valid token / zero-padded token)
+// behind its 96 channels and the packed weights carry the folded bias / the plain bias in those two k positions.
+// =================================================================================================================
+namespace {
+struct FsBars {
+  uint64_t full[4], mma;
+  uint32_t tmem_base;
+};
+constexpr int FS_C = 96, FS_K16 = 96, FS_ONES = 288, FS_NQ = 304, FS_NQ0 = 160, FS_NQ1 = 144, FS_RS = 312;
+constexpr int FS_STAGE = FS_NQ0 * 128, FS_NSTG = 4, FS_TMY = 320, FS_TMEM = 512;
+constexpr int FS_RSX = FS_C * 4 + 16;          // fp32 staging row stride in bytes (25 16-byte chunks: odd)
+constexpr int FS_KQ = 112;                     // k extent of the qkv GEMM: 96 channels + the two bias indicator columns
+constexpr int FS_U_BYTES = (132 * FS_RS * 2 + 1023) / 1024 * 1024;
+__host__ __device__ constexpr int fs_w_tile_bytes(int t) { return (t < 2 ? FS_NQ0 : (t < 4 ? FS_NQ1 : FS_C)) * 128; }
+__host__ __device__ constexpr int fs_w_tile_off(int t) {
+  return (t < 2 ? t * FS_NQ0 : (t < 4 ? 2 * FS_NQ0 + (t - 2) * FS_NQ1 : 2 * FS_NQ0 + 2 * FS_NQ1 + (t - 4) * FS_C)) * 128;
+}
+}  // namespace
+
+template <int NH>
+__global__ void __launch_bounds__(512, 1) swin_attn_stream_kernel(const FusedBlockParams p) {
+  constexpr int C = FS_C, HD = C / NH, NT = 512, NP = 4, RS = FS_RS, NQ = FS_NQ;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint8_t* a_s = smem;                                     // A tile: 2 k-blocks [128 x 64]
+  uint8_t* u_s = a_s + 2 * A_KBLOCK_BYTES;                 // q|k|v|ones rows [132][RS]
+  uint8_t* ring = u_s + FS_U_BYTES;                        // FS_NSTG weight slots
+  float* f_s = reinterpret_cast<float*>(ring + FS_NSTG * FS_STAGE);
+  const float* bproj = f_s;
+  const float4* biasfrag = reinterpret_cast<const float4*>(bproj + FS_K16);
+  int* tok_s = reinterpret_cast<int*>(f_s + FS_K16 + NH * 1024);   // [2][128]
+  float2* red = reinterpret_cast<float2*>(tok_s + 2 * 128);                  // [4][128] (mean, M2) partials
+  FsBars* bars = reinterpret_cast<FsBars*>(red + 4 * 128);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = tid & 127, part = tid >> 7;
+  if (tid == 0) {
+    for (int i = 0; i < FS_NSTG; ++i) mbar_init(&bars->full[i], 1);
+    mbar_init(&bars->mma, 1);
+    fence_barrier_init();
+  }
+  for (int i = tid * 16; i < 2 * A_KBLOCK_BYTES + FS_U_BYTES; i += NT * 16) *reinterpret_cast<uint4*>(a_s + i) = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid; i < FS_K16 + NH * 1024; i += NT) f_s[i] = p.fpk[i];
+  if (warp == 0) tmem_alloc(&bars->tmem_base, FS_TMEM);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+  const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+  const uint64_t a_desc = umma_desc_sw128(smem_u32(a_s));
+  const uint32_t idesc_q0 = umma_idesc_bf16(TILE_M, FS_NQ0), idesc_q1 = umma_idesc_bf16(TILE_M, FS_NQ1);
+  const uint32_t idesc_c = umma_idesc_bf16(TILE_M, FS_K16);
+  const int nWin2 = p.nWy * p.nWx;
+
+  // weight stream bookkeeping (warp 0 only): n_push / n_use count weight tiles since kernel start; slot = n % 4,
+  // full-barrier parity = (n / 4) & 1; the tile inside the 6-tile cycle is n % 6.
+  uint32_t n_push = 0, n_use = 0;
+  auto push = [&](int count) {   // called by every thread at the same program points; warp 0 keeps the counters
+    if (warp == 0) {
+      if (lane == 0) {
+        for (int i = 0; i < count; ++i) {
+          const uint32_t n = n_push + (uint32_t)i;
+          const int t = (int)(n % 6u), slot = (int)(n & 3u);
+          mbar_arrive_expect_tx(&bars->full[slot], (uint32_t)fs_w_tile_bytes(t));
+          bulk_g2s(ring + slot * FS_STAGE, reinterpret_cast<const uint8_t*>(p.Wpk) + fs_w_tile_off(t), (uint32_t)fs_w_tile_bytes(t),
+                   &bars->full[slot]);
+        }
+      }
+      __syncwarp();
+      n_push += (uint32_t)count;
+    }
+  };
+  auto calc_tok = [&](int tile, int slot) {
+    if (tid < 128) {
+      int tok = -1;
+      const int wl = tid / FB_TOK, t = tid - wl * FB_TOK;
+      const long long w = (long long)tile * FB_WIN + wl;
+      if (wl < FB_WIN && w < p.n_windows) {
+        const int b = (int)(w / nWin2);
+        const int wr = (int)(w - (long long)b * nWin2);
+        const int wy = wr / p.nWx, wx = wr - wy * p.nWx;
+        const int Y = wy * 5 + t / 5, X = wx * 5 + t % 5;
+        if (Y < p.H && X < p.W) tok = (b * p.H + Y) * p.W + X;
+      }
+      tok_s[slot * 128 + tid] = tok;
+    }
+  };
+  // gather the fp32 rows of a tile into the staging view of u_s ([128][FS_RSX] bytes); zero-fill for invalid tokens
+  auto issue_loads = [&](int slot) {
+    const uint32_t dst0 = smem_u32(u_s);
+#pragma unroll
+    for (int i = 0; i < 128 * (C / 4) / NT; ++i) {
+      const int q = tid + i * NT, r = q / (C / 4), c4 = q - r * (C / 4);
+      const int tok = tok_s[slot * 128 + r];
+      const float* src = tok >= 0 ? p.x + (long long)tok * C + c4 * 4 : p.x;
+      cp_async16(dst0 + r * FS_RSX + c4 * 16, src, tok >= 0 ? 16u : 0u);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  uint32_t ph_mma = 0;
+  push(4);                      // the first tile's qkv weights
+  calc_tok(blockIdx.x, 0);      // grid <= ntiles
+  __syncthreads();
+  issue_loads(0);
+
+  int it = 0;
+  for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+    const int slot = it & 1;
+    const int next = tile + gridDim.x;
+    const bool has_next = next < p.ntiles;
+    const int tokr = tok_s[slot * 128 + row];
+    // ---------------- LN1 from the staged rows: this thread owns the 16-column units {part, part + 4} ----------
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    float xv[2][16];
+    constexpr int NU = C / 16;   // 6 units per row
+#pragma unroll
+    for (int ui = 0; ui < 2; ++ui) {
+      const int cu = part + ui * NP;
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4) {
+        float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cu < NU) v4 = *reinterpret_cast<const float4*>(u_s + row * FS_RSX + (cu * 16 + j4 * 4) * 4);
+        xv[ui][j4 * 4 + 0] = v4.x; xv[ui][j4 * 4 + 1] = v4.y; xv[ui][j4 * 4 + 2] = v4.z; xv[ui][j4 * 4 + 3] = v4.w;
+      }
+    }
+    if (has_next) calc_tok(next, slot ^ 1);
+    {
+      const int nloc = part + NP < NU ? 32 : 16;
+      float sm = 0.f;
+#pragma unroll
+      for (int ui = 0; ui < 2; ++ui)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) sm += xv[ui][i];     // absent units are zeros
+      const float mloc = sm / (float)nloc;
+      float m2 = 0.f;
+#pragma unroll
+      for (int ui = 0; ui < 2; ++ui)
+        if (part + ui * NP < NU) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) m2 = fmaf(xv[ui][i] - mloc, xv[ui][i] - mloc, m2);
+        }
+      red[part * 128 + row] = make_float2(mloc, m2);
+    }
+    __syncthreads();
+    {
+      // Chan et al. combination of the four partial (mean, M2) pairs (sizes 32, 32, 16, 16)
+      float mean = 0.f;
+      float2 r2[NP];
+#pragma unroll
+      for (int pp = 0; pp < NP; ++pp) {
+        r2[pp] = red[pp * 128 + row];
+        mean += r2[pp].x * (pp + NP < NU ? 32.f : 16.f);
+      }
+      mean *= (1.0f / C);
+      float m2 = 0.f;
+#pragma unroll
+      for (int pp = 0; pp < NP; ++pp) m2 += r2[pp].y + (pp + NP < NU ? 32.f : 16.f) * (r2[pp].x - mean) * (r2[pp].x - mean);
+      const float rstd = rsqrtf(m2 * (1.0f / C) + p.eps);
+      const float nm = -mean * rstd;
+#pragma unroll
+      for (int ui = 0; ui < 2; ++ui) {
+        const int cu = part + ui * NP;
+        if (cu < NU) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            pk[i] = tokr >= 0 ? pack_op(fmaf(xv[ui][2 * i], rstd, nm), fmaf(xv[ui][2 * i + 1], rstd, nm)) : 0u;
+          const int k = cu * 16;
+          uint8_t* kb = a_s + (k >> 6) * A_KBLOCK_BYTES;
+          *reinterpret_cast<uint4*>(kb + sw128_offset(row, k & 63)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(kb + sw128_offset(row, (k & 63) + 8)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+      }
+    }
+    if (part == 2) {   // bias indicator columns 96 (valid token) / 97 (zero-padded token): k-block 1, k = 32 / 33
+      const uint32_t one_lo = pack_op(1.0f, 0.0f), one_hi = pack_op(0.0f, 1.0f);
+      *reinterpret_cast<uint4*>(a_s + A_KBLOCK_BYTES + sw128_offset(row, 32)) = make_uint4(tokr >= 0 ? one_lo : one_hi, 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(a_s + A_KBLOCK_BYTES + sw128_offset(row, 40)) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    fence_proxy_async();
+    __syncthreads();
+
+    // ---------------- qkv = LN1(x) Wqkv^T: TMEM columns [0, 160) and [160, 304) ----------------
+    if (warp == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int t = 0; t < 4; ++t, ++n_use) {
+        const int wslot = n_use & 3;
+        mbar_wait(&bars->full[wslot], (n_use >> 2) & 1u);
+        tc_fence_after();
+        if (elect_one()) {
+          const int ch = t >> 1, kb = t & 1;
+          const uint64_t bd0 = umma_desc_sw128(smem_u32(ring + wslot * FS_STAGE));
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            if (kb * 4 + ks < FS_KQ / 16)
+              umma_bf16(tmem_base + (uint32_t)(ch * FS_NQ0), a_desc + (uint64_t)(kb * (A_KBLOCK_BYTES >> 4) + ks * 2), bd0 + (uint64_t)(ks * 2),
+                        ch == 0 ? idesc_q0 : idesc_q1, (kb | ks) != 0 ? 1u : 0u);
+          }
+          if (t == 3) umma_commit(&bars->mma);
+        }
+        __syncwarp();
+      }
+      mbar_wait(&bars->mma, ph_mma);
+    }
+    ph_mma ^= 1u;
+    push(has_next ? 4 : 2);     // proj weights of this tile (+ the first half of the next tile's qkv weights)
+    __syncthreads();
+    tc_fence_after();
+    {
+      op_t* qrow = reinterpret_cast<op_t*>(u_s) + row * RS;
+      float v[16];
+#pragma unroll
+      for (int ci = 0; ci < (NQ / 16 + NP - 1) / NP; ++ci) {
+        const int cu = part + ci * NP;
+        if (cu >= NQ / 16) break;
+        tmem_ld16(lane_addr + (uint32_t)(cu * 16), v);
+        tmem_ld_wait();
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pk[i] = pack_op(v[2 * i], v[2 * i + 1]);
+        *reinterpret_cast<uint4*>(qrow + cu * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(qrow + cu * 16 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+
+    // ---------------- window attention core ----------------
+    for (int pr = warp; pr < FB_WIN * NH; pr += NT / 32) {
+      const int wl = pr / NH, h = pr - wl * NH;
+      if ((long long)tile * FB_WIN + wl >= p.n_windows) continue;
+      fb_attention_pair<HD, C, RS, FS_ONES>(u_s, a_s, biasfrag, wl, h, lane);
+    }
+    fence_proxy_async();
+    __syncthreads();
+
+    // u_s is free until the next qkv epilogue: gather the next tile's rows into it; fetch this tile's residual (L2)
+    if (has_next) issue_loads(slot ^ 1);
+    float4 xres[2][4];
+#pragma unroll
+    for (int ui = 0; ui < 2; ++ui)
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4) {
+        const int cu = part + ui * NP;
+        xres[ui][j4] = (cu < NU && tokr >= 0) ? __ldg(reinterpret_cast<const float4*>(p.x + (long long)tokr * C + cu * 16 + j4 * 4))
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+
+    // ---------------- proj ----------------
+    if (warp == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb, ++n_use) {
+        const int wslot = n_use & 3;
+        mbar_wait(&bars->full[wslot], (n_use >> 2) & 1u);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t bd0 = umma_desc_sw128(smem_u32(ring + wslot * FS_STAGE));
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            if (kb * 4 + ks < FS_K16 / 16)
+              umma_bf16(tmem_base + (uint32_t)FS_TMY, a_desc + (uint64_t)(kb * (A_KBLOCK_BYTES >> 4) + ks * 2), bd0 + (uint64_t)(ks * 2), idesc_c,
+                        (kb | ks) != 0 ? 1u : 0u);
+          }
+          if (kb == 1) umma_commit(&bars->mma);
+        }
+        __syncwarp();
+      }
+      mbar_wait(&bars->mma, ph_mma);
+    }
+    ph_mma ^= 1u;
+    if (has_next) push(2);      // second half of the next tile's qkv weights
+    __syncthreads();
+    tc_fence_after();
+    {
+      float v[16];
+#pragma unroll
+      for (int ui = 0; ui < 2; ++ui) {
+        const int cu = part + ui * NP;       // warp-uniform: the .sync.aligned TMEM load stays converged
+        if (cu < NU) {
+          tmem_ld16(lane_addr + (uint32_t)(FS_TMY + cu * 16), v);
+          tmem_ld_wait();
+          if (tokr >= 0) {
+            float* dst = p.out + (long long)tokr * C + cu * 16;
+#pragma unroll
+            for (int j4 = 0; j4 < 16; j4 += 4) {
+              const float4 x4 = xres[ui][j4 >> 2];
+              const float4 bb = *reinterpret_cast<const float4*>(bproj + cu * 16 + j4);
+              *reinterpret_cast<float4*>(dst + j4) = make_float4(x4.x + v[j4] + bb.x, x4.y + v[j4 + 1] + bb.y, x4.z + v[j4 + 2] + bb.z,
+                                                                 x4.w + v[j4 + 3] + bb.w);
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, FS_TMEM);
+  }
+}
+
+static int launch_swin_attn_stream(FusedBlockParams p, int num_sms, cudaStream_t stream) {
+  SWN_CHECK(p.C == FS_C && (p.nH == 3 || p.nH == 6) && !p.do_mlp, "swin_attn_stream: C=96, 3 or 6 heads, attention half only");
+  p.nWy = (p.H + 4) / 5;
+  p.nWx = (p.W + 4) / 5;
+  p.n_windows = (long long)p.B * p.nWy * p.nWx;
+  p.ntiles = (int)((p.n_windows + FB_WIN - 1) / FB_WIN);
+  const size_t smem = 1024 + 2 * A_KBLOCK_BYTES + FS_U_BYTES + FS_NSTG * FS_STAGE + (size_t)(FS_K16 + p.nH * 1024) * 4 +
+                      2 * 128 * 4 + 4 * 128 * 8 + sizeof(FsBars) + 64;
+  SWN_CHECK(smem <= 232448, "swin_attn_stream: shared memory overflow (%zu)", smem);
+  const int grid = p.ntiles < num_sms ? p.ntiles : num_sms;
+  auto go = [&](auto kern) -> int {
+    SWN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 512, smem, stream>>>(p);
+    SWN_CUDA(cudaGetLastError());
+    return 0;
+  };
+  return p.nH == 3 ? go(swin_attn_stream_kernel<3>) : go(swin_attn_stream_kernel<6>);
+}
+
 int launch_swin_fused(FusedBlockParams p, int num_sms, cudaStream_t stream) {
   const int C = p.C;
+  SWN_CHECK((long long)p.B * p.H * p.W < (1ll << 31), "swin_fused: token count overflows int32");
+  if (C == FS_C) return launch_swin_attn_stream(p, num_sms, stream);
   SWN_CHECK(p.B > 0 && p.H > 0 && p.W > 0 && C >= 4 && C % 4 == 0 && C <= 48 && p.nH > 0 && C % p.nH == 0,
             "swin_fused: unsupported C=%d nH=%d", C, p.nH);
   const int hd = C / p.nH;

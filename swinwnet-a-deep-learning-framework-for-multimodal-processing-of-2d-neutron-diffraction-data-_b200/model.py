@@ -155,6 +155,12 @@ class SwinTransformerBlock(nn.Module):
             return packing.pack_fused_block(*src, self.num_heads)
         return self._cache_fused.get(src, build)
 
+    def _packed_attn_stream(self):
+        a = self.attn
+        src = [self.norm1.weight, self.norm1.bias, a.qkv.weight, a.qkv.bias, a.relative_position_bias_table,
+               a.proj.weight, a.proj.bias]
+        return self._cache_fused.get(src, lambda: packing.pack_fused_attn_stream(*src, self.num_heads))
+
     def run(self, x, resolution, out, tmp=None):
         """x [B,L,C] fp32 -> out (may alias x).  `tmp` is a scratch tensor of the same shape: the attention half writes
         x + attn into it and the MLP half reads it, so no kernel ever runs in place (a thread that read-modify-writes its
@@ -179,6 +185,15 @@ class SwinTransformerBlock(nn.Module):
             return out
         pk = self._packed()
         M = B * L
+        if FUSED_BLOCK and C == 96 and self.num_heads in (3, 6) and self.shift_size == 0:
+            # attention half as one streamed-weight tcgen05 kernel (csrc/swin_fused.cu), MLP half as before
+            if tmp is None:
+                tmp = torch.empty_like(out)
+            Wpk, fpk = self._packed_attn_stream()
+            ops.swin_block_fused(x, tmp, B, H, W, C, self.num_heads, self.norm1.eps, Wpk, fpk, False)
+            Wm, b2p = pk["mlp"]
+            ops.mlp(tmp, out, M, C, pk["n2w"], pk["n2b"], Wm, pk["b1"], b2p, self.norm2.eps)
+            return out
         qkv = torch.empty(M, 3 * C, device=x.device, dtype=ops.operand_dtype())
         Wp, bp, NT, nch, nv = pk["qkv"]
         ops.rowgemm(A=x, a_mode=ops.A_F32_LN, M=M, K=C, lda=C, ln_w=pk["n1w"], ln_b=pk["n1b"], ln_eps=self.norm1.eps,

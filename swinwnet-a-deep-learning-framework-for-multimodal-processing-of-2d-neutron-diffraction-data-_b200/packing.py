@@ -175,3 +175,37 @@ def pack_fused_block(n1w, n1b, Wqkv, bqkv, table, Wproj, bproj, n2w, n2b, W1, b1
     fpk = torch.cat([qkv_bias(bq_fold), qkv_bias(bq_plain), padv(f(bproj), K16), padv(b1_fold, 4 * C), padv(f(b2), K16),
                      rel_pos_bias_fragments(f(table), LOG2E).reshape(-1)]).contiguous()
     return Wpk, fpk
+
+
+def pack_fused_attn_stream(n1w, n1b, Wqkv, bqkv, table, Wproj, bproj, num_heads: int):
+    """C = 96 attention half for csrc/swin_fused.cu::swin_attn_stream_kernel: the same folds as pack_fused_block (norm1
+    affine, q scale * log2 e, ones block at column 288, bias fragment images), with two differences:
+      * the qkv bias rides in the GEMM: k columns 96 / 97 of the packed Wqkv hold the folded bias (applied to valid
+        tokens) / the plain bias (applied to zero-padded window tokens); the kernel puts the matching indicator
+        columns into its A tile;
+      * the weights are emitted as the six [rows x 64] SWIZZLE_128B tiles the kernel streams per token tile, in
+        consumption order: Wqkv rows [0,160) k-block 0, k-block 1; rows [160,304) k-block 0, k-block 1; Wproj kb 0, 1.
+    fpk = [bproj (96) | bias fragments (nH*1024)]."""
+    C = Wqkv.shape[1]
+    assert C == 96 and Wqkv.shape[0] == 288
+    NQ, NQ0, ones_col = 304, 160, 288
+    dev = Wqkv.device
+    LOG2E = 1.4426950408889634
+    qs = (C // num_heads) ** -0.5 * LOG2E
+    f = lambda t: t.detach().float()
+    Wq, bq_plain = f(Wqkv).clone(), f(bqkv).clone()
+    Wq[:C] *= qs
+    bq_plain[:C] *= qs
+    bq_fold = bq_plain + Wq @ f(n1b)
+    Wq = Wq * f(n1w)[None, :]
+    Wz = torch.zeros(NQ, 128, device=dev)
+    Wz[:3 * C, :C] = Wq
+    Wz[:3 * C, C] = bq_fold
+    Wz[:3 * C, C + 1] = bq_plain
+    Wz[ones_col:ones_col + 8, C:C + 2] = 1.0
+    Pz = torch.zeros(C, 128, device=dev)
+    Pz[:, :C] = f(Wproj)
+    tiles = [Wz[:NQ0, :64], Wz[:NQ0, 64:], Wz[NQ0:, :64], Wz[NQ0:, 64:], Pz[:, :64], Pz[:, 64:]]
+    Wpk = torch.cat([swizzle_tiles(t.contiguous()).reshape(-1) for t in tiles]).contiguous()
+    fpk = torch.cat([f(bproj).reshape(-1), rel_pos_bias_fragments(f(table), LOG2E).reshape(-1)]).contiguous()
+    return Wpk, fpk

@@ -312,6 +312,25 @@ def test_swin_block_fused(C, nH, B, H, W, do_mlp):
     assert relerr(out, ref) <= TOL_BF16 / 4
 
 
+@pytest.mark.parametrize("nH,B,H,W", [(3, 2, 10, 15), (6, 1, 13, 9), (3, 1, 63, 120), (6, 2, 100, 101)])
+def test_swin_attn_stream_c96(nH, B, H, W):
+    """streamed-weight C=96 attention-half kernel: x + proj(W-MSA(LN1 x)) against the oracle (padding, ragged last
+    tile, several tiles per persistent CTA so that the weight ring wraps)."""
+    C = 96
+    x = rnd(B, H * W, C, seed=1) * 1.5 + 0.2
+    sd, _ = _block_sd(C, nH)
+    ref = x + O.window_attention(sd, "attn.", O.layer_norm(x, sd["norm1.weight"], sd["norm1.bias"]), (H, W), nH, 0)
+    d = {k: v.to(DEV) for k, v in sd.items()}
+    Wpk, fpk = packing.pack_fused_attn_stream(d["norm1.weight"], d["norm1.bias"], d["attn.qkv.weight"], d["attn.qkv.bias"],
+                                              d["attn.relative_position_bias_table"], d["attn.proj.weight"],
+                                              d["attn.proj.bias"], nH)
+    xd = x.to(DEV)
+    out = torch.full_like(xd, float("nan"))
+    ops.swin_block_fused(xd, out, B, H, W, C, nH, 1e-5, Wpk, fpk, False)
+    torch.cuda.synchronize()
+    assert relerr(out, ref) <= TOL_BF16 / 4
+
+
 def test_copy_cols():
     src = rnd(37, 48, seed=1).to(DEV)
     dst = torch.zeros(37, 96, device=DEV)
