@@ -40,13 +40,9 @@ def peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
 
 
-def mlp_flops_per_diffraction():
-    """16*M*C^2 per fused-MLP launch (fc1 + fc2), summed over the 52 blocks of one pipeline pass."""
-    enc = [(30000, 48), (7560, 96), (1920, 192), (480, 384)]
-    dec = [(1920, 384), (7560, 192), (30000, 96)]
-    per_pass = sum(2 * 16 * m * c * c for m, c in enc + [(480, 384)] + dec)        # depth 2 each
-    sr_head = sum(2 * 16 * m * c * c for m, c in [(120000, 24), (480000, 12)])
-    return 3 * per_pass + sr_head
+# dram__bytes_read.sum + dram__bytes_write.sum per step of the kernel family, summed over its launches, from the
+# `ncu --set full` captures summarised under profiles/ (null = not captured for this build)
+TRAFFIC_NCU = {"fused": None, "mlp": None}
 
 
 def shard_bounds(n_items, rank, world):
@@ -168,16 +164,33 @@ def main():
     out_host = torch.empty(B, 2, 2 * H, 2 * W).pin_memory()
     W_ = max(args.warmup, 3)
 
-    # ---- fused-MLP kernel timing hook (the dominant kernel: 57 % of the FLOPs) ----
-    mlp_events = []
-    orig_mlp = ops.mlp
+    # ---- per-kernel-family timing hooks (CUDA events on the launching stream, inside the timed region) ----
+    # fused = swn::swin_fused_kernel / swin_attn_stream_kernel (W-MSA [+ MLP] in one tcgen05 kernel, C <= 96),
+    # mlp   = swn::mlp_kernel / mlp_persist_kernel (LN + fc1 + GELU + fc2 + residual, C >= 96)
+    fam = {"fused": {"ev": [], "flop": 0.0, "bytes": 0.0}, "mlp": {"ev": [], "flop": 0.0, "bytes": 0.0}}
+    orig = {"fused": ops.swin_block_fused, "mlp": ops.mlp}
 
-    def timed_mlp(*a, **k):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        orig_mlp(*a, **k)
-        e1.record()
-        mlp_events.append((e0, e1))
+    def hook(name, work):
+        fn = orig[name]
+
+        def timed_op(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn(*a, **k)
+            e1.record()
+            fl, by = work(*a, **k)
+            fam[name]["ev"].append((e0, e1))
+            fam[name]["flop"] += fl
+            fam[name]["bytes"] += by
+        return timed_op
+
+    def fused_work(x, out, Bn, Hn, Wn, C, nH, eps, Wpk, fpk, do_mlp=True):
+        M = Bn * Hn * Wn      # algorithmic FLOPs of a block: 24 C^2 + 100 C per token (8 C^2 + 100 C for the W-MSA half)
+        return ((24.0 if do_mlp else 8.0) * C * C + 100.0 * C) * M, 8.0 * M * C
+
+    def mlp_work(x, out, M, C, *a, **k):
+        return 16.0 * M * C * C, 8.0 * M * C
+    hooks = {"fused": hook("fused", fused_work), "mlp": hook("mlp", mlp_work)}
 
     def barrier():
         torch.cuda.synchronize()
@@ -207,14 +220,23 @@ def main():
         step_dev()
     sampler = ClockSampler(local)
     sampler.start()
-    ops.mlp = timed_mlp
-    S.model.ops.mlp = timed_mlp
+    ops.swin_block_fused, ops.mlp = hooks["fused"], hooks["mlp"]
     n0 = ops.LAUNCH_COUNT
     ms = timed(step_dev, args.steps)
     launches = ops.LAUNCH_COUNT - n0
-    ops.mlp = orig_mlp
-    S.model.ops.mlp = orig_mlp
-    mlp_ms = sum(a.elapsed_time(b) for a, b in mlp_events) / args.steps
+    ops.swin_block_fused, ops.mlp = orig["fused"], orig["mlp"]
+    pk = peaks()
+    kern = {}
+    for name, label in (("fused", "swn::swin_fused_kernel + swin_attn_stream_kernel (fused LN1+qkv+W-MSA+proj[+LN2+MLP], C<=96)"),
+                        ("mlp", "swn::mlp_kernel + mlp_persist_kernel (fused LN2+fc1+GELU+fc2+residual, C>=96)")):
+        f = fam[name]
+        k_ms = sum(a.elapsed_time(b) for a, b in f["ev"]) / args.steps
+        tf = f["flop"] / args.steps / (k_ms / 1e3) / 1e12 if k_ms > 0 else 0.0
+        gbs = f["bytes"] / args.steps / (k_ms / 1e3) / 1e9 if k_ms > 0 else 0.0
+        kern[name] = {"kernel": label, "launches_per_step": len(f["ev"]) // max(args.steps, 1), "kernel_ms_per_step": k_ms,
+                      "kernel_share_of_step": k_ms / (ms / args.steps), "achieved_tflops": tf, "tensor_frac": tf / pk["tf_sust"],
+                      "achieved_gbs": gbs, "hbm_frac": gbs / pk["hbm"]}
+    dom = max(kern, key=lambda n: kern[n]["kernel_ms_per_step"])
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
@@ -223,8 +245,6 @@ def main():
 
     value = whole_job_rate(B, world, args.steps, ms)
     e2e_v = whole_job_rate(B, world, args.steps, ms_e2e)
-    pk = peaks()
-    mlp_tflops = mlp_flops_per_diffraction() * B / (mlp_ms / 1e3) / 1e12
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W_,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if ops.operand_dtype() == torch.bfloat16 else "fp16", "data": "synthetic",
@@ -235,10 +255,13 @@ def main():
             "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4,
                     "d2h_bytes_per_step": out_host.numel() * 4},
             "gpu_launches": launches,
-            "roofline": {"bound": "tensor", "kernel": "swn::mlp_kernel (fused LN+fc1+GELU+fc2+residual)",
-                         "achieved": mlp_tflops, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": mlp_tflops / pk["tf_sust"],
-                         "traffic": None, "peak_source": pk["src"] + " (sustained bf16)",
-                         "kernel_ms_per_step": mlp_ms, "kernel_share_of_step": mlp_ms / (ms / args.steps)},
+            "roofline": {"bound": "tensor", "kernel": kern[dom]["kernel"], "achieved": kern[dom]["achieved_tflops"],
+                         "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": kern[dom]["tensor_frac"],
+                         "traffic": TRAFFIC_NCU.get(dom), "peak_source": pk["src"] + " (sustained bf16)",
+                         "kernel_ms_per_step": kern[dom]["kernel_ms_per_step"],
+                         "kernel_share_of_step": kern[dom]["kernel_share_of_step"],
+                         "hbm_achieved_gbs": kern[dom]["achieved_gbs"], "hbm_peak_gbs": pk["hbm"], "hbm_frac": kern[dom]["hbm_frac"]},
+            "kernels": kern,
             "clocks": sampler.summary()}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count()

@@ -79,6 +79,10 @@ int swn_swin_block_small(const float* x, float* out, int B, int H, int W, int C,
 int swn_swin_block_fused(const float* x, float* out, int B, int H, int W, int C, int num_heads, float eps,
                          const void* Wpk, const float* fpk, int do_mlp, void* stream);
 
+/* Profiling aid: when set to a device buffer of [grid][16] int64 (zeroed by the caller), the fused block kernels add the
+ * clock64 cycles thread 0 of each CTA spends in each barrier-delimited phase.  NULL (default) disables it. */
+int swn_set_phase_profile(void* device_buffer);
+
 /* 5x5 (shifted-)window attention core on token-ordered qkv (SwinWNet.py:86-149,183-206,246-272). */
 int swn_window_attention(const void* qkv_bf16, void* out_bf16, const float* qkv_bias, const float* rpb_table,
                          int B, int H, int W, int C, int num_heads, int shift, void* stream);

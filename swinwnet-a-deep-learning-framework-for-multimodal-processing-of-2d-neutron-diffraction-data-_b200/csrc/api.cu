@@ -23,6 +23,7 @@ static void mlp_config(int C, int* HC, int* TR) {
   else *HC = Hd;
   *TR = C16 <= 256 ? C16 : C16 / 2;
 }
+static long long* g_phase_cycles = nullptr;
 static int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -100,7 +101,13 @@ int swn_swin_block_fused(const float* x, float* out, int B, int H, int W, int C,
   FusedBlockParams p{};
   p.x = x; p.out = out; p.B = B; p.H = H; p.W = W; p.C = C; p.nH = num_heads; p.eps = eps;
   p.Wpk = reinterpret_cast<const op_t*>(Wpk); p.fpk = fpk; p.do_mlp = do_mlp;
+  p.phase_cycles = g_phase_cycles;
   return launch_swin_fused(p, num_sms(), reinterpret_cast<cudaStream_t>(stream));
+}
+
+int swn_set_phase_profile(void* device_buffer) {
+  g_phase_cycles = reinterpret_cast<long long*>(device_buffer);
+  return 0;
 }
 
 int swn_window_attention(const void* qkv, void* out, const float* qkv_bias, const float* rpb_table, int B, int H, int W,

@@ -97,6 +97,7 @@ struct FusedBlockParams {   // fused W-MSA (+ MLP) block, shift 0, resident pack
   int w_bytes, nf, u_bytes;
   int off_a, off_u, off_stage, off_f, off_misc;
   int tm_y, tmem_cols;
+  long long* phase_cycles;   // optional [grid][16] per-phase clock64 sums written by thread 0 of each CTA (profiling aid)
 };
 int launch_swin_fused(FusedBlockParams p, int num_sms, cudaStream_t stream);
 

@@ -286,20 +286,28 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
         uint8_t* hrow = hs_smem + buf * nkk * A_KBLOCK_BYTES;
         const float* bj = b1s + j * HC;
         const uint32_t t_chunk = lane_addr + (uint32_t)(hbase + buf * HC);
-        for (int cb = cb_beg; cb < cb_end; ++cb) {
-          tmem_ld16(t_chunk + cb * 16, v);
-          tmem_ld_wait();
-          const int k = cb * 16;
-          uint32_t pk[8];
+        // all TMEM loads of this thread's blocks are issued before the first GELU (one exposed TMEM round trip per chunk)
+        float vv[4][16];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 bb = *reinterpret_cast<const float4*>(bj + k + 4 * i);
-            pk[2 * i] = pack_op(gelu_fast(v[4 * i] + bb.x), gelu_fast(v[4 * i + 1] + bb.y));
-            pk[2 * i + 1] = pack_op(gelu_fast(v[4 * i + 2] + bb.z), gelu_fast(v[4 * i + 3] + bb.w));
+        for (int i = 0; i < 4; ++i)
+          if (cb_beg + i < cb_end) tmem_ld16(t_chunk + (cb_beg + i) * 16, vv[i]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int cb = cb_beg + i;
+          if (cb < cb_end) {
+            const int k = cb * 16;
+            uint32_t pk[8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 bb = *reinterpret_cast<const float4*>(bj + k + 4 * q);
+              pk[2 * q] = pack_op(gelu_fast(vv[i][4 * q] + bb.x), gelu_fast(vv[i][4 * q + 1] + bb.y));
+              pk[2 * q + 1] = pack_op(gelu_fast(vv[i][4 * q + 2] + bb.z), gelu_fast(vv[i][4 * q + 3] + bb.w));
+            }
+            uint8_t* kb_base = hrow + (k >> 6) * A_KBLOCK_BYTES;
+            *reinterpret_cast<uint4*>(kb_base + sw128_offset(r, k & 63)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(kb_base + sw128_offset(r, (k & 63) + 8)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           }
-          uint8_t* kb_base = hrow + (k >> 6) * A_KBLOCK_BYTES;
-          *reinterpret_cast<uint4*>(kb_base + sw128_offset(r, k & 63)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *reinterpret_cast<uint4*>(kb_base + sw128_offset(r, (k & 63) + 8)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         }
         tc_fence_before();
         fence_proxy_async();
@@ -350,6 +358,11 @@ int launch_mlp_persist(MlpParams p, int num_sms, cudaStream_t stream) {
   int cols = ((C16 + 31) & ~31) + (nj > 1 ? 2 : 1) * p.HC, tc = 32;
   while (tc < cols) tc <<= 1;
   SWN_CHECK(tc <= 512, "mlp_persist: TMEM overflow");
+  {
+    const int steps2 = p.HC >> 4;   // 16-column blocks per hidden chunk; an epilogue thread keeps at most 4 in registers
+    SWN_CHECK((steps2 % MP_EPI_SPLIT == 0 ? steps2 / MP_EPI_SPLIT : (steps2 % 2 == 0 ? steps2 / 2 : steps2)) <= 4,
+              "mlp_persist: hidden chunk HC=%d too wide for the epilogue register tile", p.HC);
+  }
   p.tmem_cols = tc;
   const int chunks = C / 4;
   p.row_stride = (chunks + ((chunks & 1) ? 0 : 1)) * 16;

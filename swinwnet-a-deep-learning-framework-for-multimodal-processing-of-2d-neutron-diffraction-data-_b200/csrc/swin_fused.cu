@@ -771,6 +771,18 @@ __global__ void __launch_bounds__(512, 1) swin_attn_stream_kernel(const FusedBlo
   __syncthreads();
   issue_loads(0);
 
+  // optional phase profile: thread 0 accumulates the cycles between consecutive marks
+  long long ph_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long ph_t = 0;
+  const bool prof = p.phase_cycles != nullptr && tid == 0;
+  auto mark = [&](int i) {
+    if (prof) {
+      const long long t = clock64();
+      ph_acc[i] += t - ph_t;
+      ph_t = t;
+    }
+  };
+  if (prof) ph_t = clock64();
   int it = 0;
   for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
     const int slot = it & 1;
@@ -780,6 +792,7 @@ __global__ void __launch_bounds__(512, 1) swin_attn_stream_kernel(const FusedBlo
     // ---------------- LN1 from the staged rows: this thread owns the 16-column units {part, part + 4} ----------
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
+    mark(0);
     float xv[2][16];
     constexpr int NU = C / 16;   // 6 units per row
 #pragma unroll
@@ -811,6 +824,7 @@ __global__ void __launch_bounds__(512, 1) swin_attn_stream_kernel(const FusedBlo
       red[part * 128 + row] = make_float2(mloc, m2);
     }
     __syncthreads();
+    mark(1);
     {
       // Chan et al. combination of the four partial (mean, M2) pairs (sizes 32, 32, 16, 16)
       float mean = 0.f;
@@ -848,6 +862,7 @@ __global__ void __launch_bounds__(512, 1) swin_attn_stream_kernel(const FusedBlo
     }
     fence_proxy_async();
     __syncthreads();
+    mark(2);
 
     // ---------------- qkv = LN1(x) Wqkv^T: TMEM columns [0, 160) and [160, 304) ----------------
     if (warp == 0) {
@@ -875,6 +890,7 @@ __global__ void __launch_bounds__(512, 1) swin_attn_stream_kernel(const FusedBlo
     ph_mma ^= 1u;
     push(has_next ? 4 : 2);     // proj weights of this tile (+ the first half of the next tile's qkv weights)
     __syncthreads();
+    mark(3);
     tc_fence_after();
     {
       op_t* qrow = reinterpret_cast<op_t*>(u_s) + row * RS;
@@ -894,6 +910,7 @@ __global__ void __launch_bounds__(512, 1) swin_attn_stream_kernel(const FusedBlo
     }
     tc_fence_before();
     __syncthreads();
+    mark(4);
 
     // ---------------- window attention core ----------------
     for (int pr = warp; pr < FB_WIN * NH; pr += NT / 32) {
@@ -903,18 +920,7 @@ __global__ void __launch_bounds__(512, 1) swin_attn_stream_kernel(const FusedBlo
     }
     fence_proxy_async();
     __syncthreads();
-
-    // u_s is free until the next qkv epilogue: gather the next tile's rows into it; fetch this tile's residual (L2)
-    if (has_next) issue_loads(slot ^ 1);
-    float4 xres[2][4];
-#pragma unroll
-    for (int ui = 0; ui < 2; ++ui)
-#pragma unroll
-      for (int j4 = 0; j4 < 4; ++j4) {
-        const int cu = part + ui * NP;
-        xres[ui][j4] = (cu < NU && tokr >= 0) ? __ldg(reinterpret_cast<const float4*>(p.x + (long long)tokr * C + cu * 16 + j4 * 4))
-                                             : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+    mark(5);
 
     // ---------------- proj ----------------
     if (warp == 0) {
@@ -936,13 +942,39 @@ __global__ void __launch_bounds__(512, 1) swin_attn_stream_kernel(const FusedBlo
         }
         __syncwarp();
       }
+    }
+    mark(8);
+    // u_s is free until the next qkv epilogue: gather the next tile's rows into it; fetch this tile's residual (L2)
+    if (has_next) issue_loads(slot ^ 1);
+    // (transposed ownership for coalescing: in pass ps a lane handles 16-byte chunk lane&3 of row ps*8 + lane/4 of the
+    // warp's 32 rows, so one warp instruction touches 8 rows x 64 contiguous bytes instead of 32 rows x 16 bytes)
+    const int wrow0 = (warp & 3) * 32;
+    float4 xres[2][4];
+#pragma unroll
+    for (int ui = 0; ui < 2; ++ui)
+#pragma unroll
+      for (int ps = 0; ps < 4; ++ps) {
+        const int cu = part + ui * NP;
+        const int tok = tok_s[slot * 128 + wrow0 + ps * 8 + (lane >> 2)];
+        xres[ui][ps] = (cu < NU && tok >= 0) ? __ldg(reinterpret_cast<const float4*>(p.x + (long long)tok * C + cu * 16 + (lane & 3) * 4))
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+
+    mark(9);
+    if (warp == 0) {
       mbar_wait(&bars->mma, ph_mma);
+      mark(10);
     }
     ph_mma ^= 1u;
     if (has_next) push(2);      // second half of the next tile's qkv weights
     __syncthreads();
+    mark(6);
     tc_fence_after();
     {
+      // Y + bias goes through a per-warp 2 KB scratch (the A tile is free once the proj MMA has retired) so that the
+      // residual add and the global store run in the coalesced transposed ownership; 16-byte chunks are XOR-swizzled
+      // with (row >> 1) & 3: conflict free for the row-per-lane write and the 2-rows-per-phase read
+      uint8_t* scratch = a_s + warp * 2048;
       float v[16];
 #pragma unroll
       for (int ui = 0; ui < 2; ++ui) {
@@ -950,22 +982,32 @@ __global__ void __launch_bounds__(512, 1) swin_attn_stream_kernel(const FusedBlo
         if (cu < NU) {
           tmem_ld16(lane_addr + (uint32_t)(FS_TMY + cu * 16), v);
           tmem_ld_wait();
-          if (tokr >= 0) {
-            float* dst = p.out + (long long)tokr * C + cu * 16;
 #pragma unroll
-            for (int j4 = 0; j4 < 16; j4 += 4) {
-              const float4 x4 = xres[ui][j4 >> 2];
-              const float4 bb = *reinterpret_cast<const float4*>(bproj + cu * 16 + j4);
-              *reinterpret_cast<float4*>(dst + j4) = make_float4(x4.x + v[j4] + bb.x, x4.y + v[j4 + 1] + bb.y, x4.z + v[j4 + 2] + bb.z,
-                                                                 x4.w + v[j4 + 3] + bb.w);
-            }
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 bb = *reinterpret_cast<const float4*>(bproj + cu * 16 + j4 * 4);
+            *reinterpret_cast<float4*>(scratch + lane * 64 + ((j4 ^ ((lane >> 1) & 3)) << 4)) =
+                make_float4(v[j4 * 4] + bb.x, v[j4 * 4 + 1] + bb.y, v[j4 * 4 + 2] + bb.z, v[j4 * 4 + 3] + bb.w);
           }
+          __syncwarp();
+#pragma unroll
+          for (int ps = 0; ps < 4; ++ps) {
+            const int rl = ps * 8 + (lane >> 2), c = lane & 3;
+            const int tok = tok_s[slot * 128 + wrow0 + rl];
+            const float4 y = *reinterpret_cast<const float4*>(scratch + rl * 64 + ((c ^ ((rl >> 1) & 3)) << 4));
+            const float4 x4 = xres[ui][ps];
+            if (tok >= 0)
+              *reinterpret_cast<float4*>(p.out + (long long)tok * C + cu * 16 + c * 4) = make_float4(x4.x + y.x, x4.y + y.y, x4.z + y.z, x4.w + y.w);
+          }
+          __syncwarp();
         }
       }
     }
     tc_fence_before();
     __syncthreads();
+    mark(7);
   }
+  if (prof)
+    for (int i = 0; i < 12; ++i) p.phase_cycles[(long long)blockIdx.x * 16 + i] += ph_acc[i];
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, FS_TMEM);

@@ -88,6 +88,12 @@ def swin_block_fused(x, out, B, H, W, C, nH, eps, Wpk, fpk, do_mlp=True):
     _count("swin_block_fused")
 
 
+def set_phase_profile(buf):
+    """profiling aid: int64 device tensor [grid, 16] (zeroed) that the fused block kernels add per-phase cycles to;
+    None disables it."""
+    _lib.check(_lib.load().swn_set_phase_profile(_ptr(buf)), "swn_set_phase_profile")
+
+
 def window_attention(qkv, out, qkv_bias, table, B, H, W, C, nH, shift=0):
     _need_cuda(qkv, out)
     _lib.check(_lib.load().swn_window_attention(_ptr(qkv), _ptr(out), _ptr(qkv_bias), _ptr(table), B, H, W, C, nH, shift,
