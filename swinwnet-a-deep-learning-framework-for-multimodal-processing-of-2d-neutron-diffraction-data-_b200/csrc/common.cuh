@@ -284,6 +284,28 @@ __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t k) {
   return row * 128u + ((((k >> 3) ^ row) & 7u) << 4) + ((k & 7u) << 1);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Coalesced epilogue I/O.  After tcgen05.ld a lane holds 16 consecutive fp32 columns of ITS row, so a direct
+// 16-byte global access per lane touches 32 different rows per warp instruction: 32 half-used sectors, and the SM
+// injects only ~1 sector request per cycle (measured: this pattern alone cost ~45 % of the proj-GEMM time).  The warp
+// therefore transposes the 32 x 16 block through 2 KB of shared memory (16-byte chunks XOR-swizzled with
+// (row >> 1) & 3: conflict free both ways); afterwards lane l owns chunk l&3 of rows ps*8 + l/4, ps = 0..3, i.e. one
+// warp instruction covers 8 rows x 64 contiguous bytes (fully used sectors).  All lanes of the warp must call these.
+// ---------------------------------------------------------------------------------------------
+constexpr int EPI_SCRATCH_BYTES = 2048;   // per warp
+__device__ __forceinline__ void epi_scatter16(uint8_t* scratch, const float* v, int lane) {
+#pragma unroll
+  for (int j4 = 0; j4 < 4; ++j4)
+    *reinterpret_cast<float4*>(scratch + lane * 64 + ((j4 ^ ((lane >> 1) & 3)) << 4)) =
+        make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+  __syncwarp();
+}
+// chunk (lane & 3) of row ps*8 + (lane >> 2) of the block written by epi_scatter16
+__device__ __forceinline__ float4 epi_gather4(const uint8_t* scratch, int ps, int lane) {
+  const int rl = ps * 8 + (lane >> 2), c = lane & 3;
+  return *reinterpret_cast<const float4*>(scratch + rl * 64 + ((c ^ ((rl >> 1) & 3)) << 4));
+}
+
 constexpr int TILE_M = 128;                 // rows per CTA tile = UMMA M
 constexpr int KBLK = 64;                    // bf16 elements per swizzle row
 constexpr int A_KBLOCK_BYTES = TILE_M * 128;  // one [128 x 64] bf16 k-block

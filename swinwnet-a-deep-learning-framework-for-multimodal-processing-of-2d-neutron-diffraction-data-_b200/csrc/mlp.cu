@@ -200,7 +200,6 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(const MlpParams p) 
     const int half = (warp - 2) >> 2;
     const int r = lg * 32 + lane;
     const long long m = m0 + r;
-    const bool row_ok = m < p.M;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
     // 16-column blocks of the hidden chunk owned by this warp
     const int cb_beg = (steps2 & 1) ? (half ? steps2 : 0) : half * (steps2 >> 1);
@@ -243,24 +242,27 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(const MlpParams p) 
     }
     mbar_wait(&sh->y_full, 0);
     tc_fence_after();
+    // transposed ownership for the residual read and the store (common.cuh); the hidden tiles are free by now and
+    // serve as the per-warp 2 KB scratch
+    uint8_t* scr = hs_smem + (warp - 2) * EPI_SCRATCH_BYTES;
     for (int cb = half; cb < (C16 >> 4); cb += 2) {
       tmem_ld16(lane_addr + (uint32_t)(cb * 16), v);
       tmem_ld_wait();
-      if (row_ok) {
 #pragma unroll
-        for (int j4 = 0; j4 < 16; j4 += 4) {
-          const int c = cb * 16 + j4;
-          if (c < C) {
-            const float4 xr = *reinterpret_cast<const float4*>(p.x + m * C + c);
-            float4 o;
-            o.x = v[j4 + 0] + b2s[c + 0] + xr.x;
-            o.y = v[j4 + 1] + b2s[c + 1] + xr.y;
-            o.z = v[j4 + 2] + b2s[c + 2] + xr.z;
-            o.w = v[j4 + 3] + b2s[c + 3] + xr.w;
-            *reinterpret_cast<float4*>(p.out + m * C + c) = o;
-          }
+      for (int j = 0; j < 16; ++j) v[j] += b2s[cb * 16 + j];
+      epi_scatter16(scr, v, lane);
+      const int c = cb * 16 + (lane & 3) * 4;
+      if (c < C) {
+#pragma unroll
+        for (int ps = 0; ps < 4; ++ps) {
+          const long long mm = m0 + lg * 32 + ps * 8 + (lane >> 2);
+          if (mm >= p.M) continue;
+          const float4 y = epi_gather4(scr, ps, lane);
+          const float4 xr = __ldg(reinterpret_cast<const float4*>(p.x + mm * C + c));
+          *reinterpret_cast<float4*>(p.out + mm * C + c) = make_float4(y.x + xr.x, y.y + xr.y, y.z + xr.z, y.w + xr.w);
         }
       }
+      __syncwarp();
     }
   }
   tc_fence_before();

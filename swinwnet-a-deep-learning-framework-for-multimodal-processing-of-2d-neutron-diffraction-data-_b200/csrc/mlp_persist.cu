@@ -276,7 +276,6 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int s = it & 1;
       const long long m = (long long)tile * TILE_M + r;
-      const bool row_ok = m < p.M;
       for (int j = 0; j < nj; ++j) {
         const int g = it * nj + j, buf = g & 1;
         const uint32_t ph = ((uint32_t)g >> 1) & 1u;
@@ -317,23 +316,30 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
       // final: Y + b2 + residual(staging) -> out
       mbar_wait(&sh->y_full, (uint32_t)it & 1u);
       tc_fence_after();
-      const uint8_t* res = stg + s * TILE_M * rs + r * rs;
+      // out = Y + b2 + residual is formed in place in the staging row (row-per-lane, conflict free), then stored in the
+      // transposed ownership (common.cuh): 8 rows x 64 contiguous bytes per warp instruction
+      uint8_t* stile = stg + s * TILE_M * rs;
+      uint8_t* res = stile + r * rs;
       for (int cb = part; cb < (C16 >> 4); cb += MP_EPI_SPLIT) {
         tmem_ld16(lane_addr + (uint32_t)(cb * 16), v);
         tmem_ld_wait();
-        if (row_ok) {
 #pragma unroll
-          for (int j4 = 0; j4 < 16; j4 += 4) {
-            const int c = cb * 16 + j4;
-            if (c < C) {
-              const float4 xr = *reinterpret_cast<const float4*>(res + c * 4);
-              float4 o;
-              o.x = v[j4 + 0] + b2s[c + 0] + xr.x;
-              o.y = v[j4 + 1] + b2s[c + 1] + xr.y;
-              o.z = v[j4 + 2] + b2s[c + 2] + xr.z;
-              o.w = v[j4 + 3] + b2s[c + 3] + xr.w;
-              *reinterpret_cast<float4*>(p.out + m * C + c) = o;
-            }
+        for (int j4 = 0; j4 < 16; j4 += 4) {
+          const int c = cb * 16 + j4;
+          if (c < C) {
+            const float4 xr = *reinterpret_cast<const float4*>(res + c * 4);
+            *reinterpret_cast<float4*>(res + c * 4) =
+                make_float4(v[j4 + 0] + b2s[c + 0] + xr.x, v[j4 + 1] + b2s[c + 1] + xr.y, v[j4 + 2] + b2s[c + 2] + xr.z, v[j4 + 3] + b2s[c + 3] + xr.w);
+          }
+        }
+        __syncwarp();
+        const int c = cb * 16 + (lane & 3) * 4;
+        if (c < C) {
+#pragma unroll
+          for (int ps = 0; ps < 4; ++ps) {
+            const int rl = lg * 32 + ps * 8 + (lane >> 2);
+            const long long mm = (long long)tile * TILE_M + rl;
+            if (mm < p.M) *reinterpret_cast<float4*>(p.out + mm * C + c) = *reinterpret_cast<const float4*>(stile + rl * rs + c * 4);
           }
         }
       }
