@@ -165,6 +165,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Pure polling wait (mbarrier.test_wait, never suspends): for the single warp that watches an MMA-completion barrier
+// while the rest of the CTA is parked at a CTA barrier, the wake-up latency of the suspending try_wait form is on the
+// critical path of every tile; spinning costs nothing there.  Bounded like mbar_wait.
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok = 0, tries = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (!ok && (++tries & 0xfffffu) == 0 && tries > 0x40000000u) {
+      printf("swn: mbarrier spin timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  } while (!ok);
+}
+
 // ---------------------------------------------------------------------------------------------
 // async proxy: bulk copy global -> shared (TMA engine, 1-D), proxy fence
 // ---------------------------------------------------------------------------------------------

@@ -179,7 +179,7 @@ __device__ __forceinline__ void fb_attention_pair(const uint8_t* u_s, uint8_t* a
     }
 }
 
-template <int CC, int NH, int NT, int MINB>
+template <int CC, int NH, int NT, int MINB, bool PROF>
 __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockParams p) {
   using G = FbGeom<CC>;
   constexpr int HD = CC / NH;
@@ -317,6 +317,21 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
   };
   constexpr float inv_c = 1.0f / (float)C;
   int it = 0;
+  // optional phase profile (tools/phase_profile.py): thread 0 accumulates the cycles between consecutive marks
+  __shared__ long long ph_acc[PROF ? 16 : 1];
+  long long ph_t = 0;
+  const bool prof = PROF && tid == 0;
+  auto mark = [&](int i) {
+    if constexpr (PROF) if (prof) {
+      const long long t = clock64();
+      ph_acc[i] += t - ph_t;
+      ph_t = t;
+    }
+  };
+  if constexpr (PROF) if (prof) {
+    for (int i = 0; i < 16; ++i) ph_acc[i] = 0;
+    ph_t = clock64();
+  }
   const bool prefetch = p.n_stage == 2;
   calc_tok(blockIdx.x, 0);     // grid <= ntiles
   __syncthreads();
@@ -328,6 +343,7 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
     const bool has_next = next < p.ntiles;
     if (has_next) calc_tok(next, (it + 1) % 3);
     __syncthreads();   // previous tile's write-back finished everywhere; tok of the next tile visible
+    mark(0);
     if (prefetch) {
       if (has_next) {
         issue_loads((it + 1) % 3, buf ^ 1);
@@ -340,6 +356,7 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
       asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();   // this tile's rows are in stg[buf]
+    mark(1);
 
     uint8_t* stile = stg + buf * 128 * RSB;
     uint8_t* srow = stile + row * RSB;
@@ -361,6 +378,7 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
       red[part * 128 + row] = make_float2(s1, s2);
     }
     __syncthreads();
+    mark(2);
     {
       float t1 = 0.f, t2 = 0.f;
 #pragma unroll
@@ -375,6 +393,7 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
     }
     fence_proxy_async();
     __syncthreads();
+    mark(3);
 
     // ---------------- qkv = LN1(x) Wqkv^T  (TMEM columns [0, NQ)) ----------------
     if (warp == 0) {
@@ -396,6 +415,7 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
     }
     wait_bar(&bars->mma, 0);
     __syncthreads();
+    mark(4);
     tc_fence_after();
     {
       op_t* qrow = reinterpret_cast<op_t*>(u_s) + row * RS;
@@ -416,6 +436,7 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
     }
     tc_fence_before();
     __syncthreads();
+    mark(5);
 
     // ---------------- window attention core: one (window, head) pair per warp pass ----------------
     for (int pr = warp; pr < FB_WIN * nH; pr += NT / 32) {
@@ -425,6 +446,7 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
     }
     fence_proxy_async();
     __syncthreads();
+    mark(6);
 
     // ---------------- proj: Y = O Wproj^T (TMEM columns [tm_y, tm_y + K16)) ----------------
     if (warp == 0) {
@@ -442,6 +464,7 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
     }
     wait_bar(&bars->mma, 0);
     __syncthreads();
+    mark(7);
     tc_fence_after();
     {
       // x1 = x + proj + bias, written back to the staging row; partial LN2 moments on the fly
@@ -475,6 +498,7 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
     }
     tc_fence_before();
     __syncthreads();
+    mark(8);
 
     if (p.do_mlp) {
       // ---------------- LN2 ----------------
@@ -492,6 +516,7 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
       }
       fence_proxy_async();
       __syncthreads();
+      mark(9);
 
       // ---------------- MLP: all GEMM1 chunks are issued at once (TMEM columns [j*HCp, j*HCp + HC)); the GELU epilogue
       // of chunk j fills hidden tile j and GEMM2(j) accumulates Y behind it, so only two MMA round trips are exposed ----
@@ -512,6 +537,7 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
       }
       wait_bar(&bars->g1[0], 1);
       __syncthreads();
+      mark(10);
       tc_fence_after();
       if constexpr (NHS == nj && nj > 1) {
         // one hidden tile per chunk: all GELU epilogues back to back (TMEM loads of every chunk in flight before the
@@ -545,6 +571,7 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
         tc_fence_before();
         fence_proxy_async();
         __syncthreads();
+        mark(11);
         if (warp == 0) {
           tc_fence_after();
           if (elect_one()) {
@@ -566,6 +593,7 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
         if (j > 0) {   // single hidden tile: wait until GEMM2(j-1) has consumed it
           wait_bar(&bars->g2[0], 3);
           __syncthreads();
+          mark(12);
         }
         uint8_t* hs = u_s;
         {
@@ -588,6 +616,7 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
         tc_fence_before();
         fence_proxy_async();
         __syncthreads();
+        mark(13);
         if (warp == 0) {
           tc_fence_after();
           if (elect_one()) {
@@ -604,6 +633,7 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
       }
       wait_bar(&bars->g2[0], 3);
       __syncthreads();
+      mark(14);
       tc_fence_after();
       {
         float v[16];
@@ -627,6 +657,7 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
       }
       tc_fence_before();
       __syncthreads();
+      mark(15);
     }
 
     // ---------------- coalesced write-back of the valid token rows ----------------
@@ -646,6 +677,8 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
     }
   }
 
+  if constexpr (PROF) if (prof)
+    for (int i = 0; i < 16; ++i) p.phase_cycles[(long long)blockIdx.x * 16 + i] += ph_acc[i];
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -684,7 +717,7 @@ __host__ __device__ constexpr int fs_w_tile_off(int t) {
 }
 }  // namespace
 
-template <int NH>
+template <int NH, bool PROF>
 __global__ void __launch_bounds__(512, 1) swin_attn_stream_kernel(const FusedBlockParams p) {
   constexpr int C = FS_C, HD = C / NH, NT = 512, NP = 4, RS = FS_RS, NQ = FS_NQ;
   extern __shared__ uint8_t smem_raw[];
@@ -772,17 +805,20 @@ __global__ void __launch_bounds__(512, 1) swin_attn_stream_kernel(const FusedBlo
   issue_loads(0);
 
   // optional phase profile: thread 0 accumulates the cycles between consecutive marks
-  long long ph_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  __shared__ long long ph_acc[PROF ? 12 : 1];
   long long ph_t = 0;
-  const bool prof = p.phase_cycles != nullptr && tid == 0;
+  const bool prof = PROF && tid == 0;
   auto mark = [&](int i) {
-    if (prof) {
+    if constexpr (PROF) if (prof) {
       const long long t = clock64();
       ph_acc[i] += t - ph_t;
       ph_t = t;
     }
   };
-  if (prof) ph_t = clock64();
+  if constexpr (PROF) if (prof) {
+    for (int i = 0; i < 12; ++i) ph_acc[i] = 0;
+    ph_t = clock64();
+  }
   int it = 0;
   for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
     const int slot = it & 1;
@@ -885,7 +921,7 @@ __global__ void __launch_bounds__(512, 1) swin_attn_stream_kernel(const FusedBlo
         }
         __syncwarp();
       }
-      mbar_wait(&bars->mma, ph_mma);
+      mbar_wait_spin(&bars->mma, ph_mma);
     }
     ph_mma ^= 1u;
     push(has_next ? 4 : 2);     // proj weights of this tile (+ the first half of the next tile's qkv weights)
@@ -962,7 +998,7 @@ __global__ void __launch_bounds__(512, 1) swin_attn_stream_kernel(const FusedBlo
 
     mark(9);
     if (warp == 0) {
-      mbar_wait(&bars->mma, ph_mma);
+      mbar_wait_spin(&bars->mma, ph_mma);
       mark(10);
     }
     ph_mma ^= 1u;
@@ -1006,7 +1042,7 @@ __global__ void __launch_bounds__(512, 1) swin_attn_stream_kernel(const FusedBlo
     __syncthreads();
     mark(7);
   }
-  if (prof)
+  if constexpr (PROF) if (prof)
     for (int i = 0; i < 12; ++i) p.phase_cycles[(long long)blockIdx.x * 16 + i] += ph_acc[i];
   if (warp == 0) {
     tc_fence_after();
@@ -1030,7 +1066,8 @@ static int launch_swin_attn_stream(FusedBlockParams p, int num_sms, cudaStream_t
     SWN_CUDA(cudaGetLastError());
     return 0;
   };
-  return p.nH == 3 ? go(swin_attn_stream_kernel<3>) : go(swin_attn_stream_kernel<6>);
+  if (p.phase_cycles) return p.nH == 3 ? go(swin_attn_stream_kernel<3, true>) : go(swin_attn_stream_kernel<6, true>);
+  return p.nH == 3 ? go(swin_attn_stream_kernel<3, false>) : go(swin_attn_stream_kernel<6, false>);
 }
 
 int launch_swin_fused(FusedBlockParams p, int num_sms, cudaStream_t stream) {
@@ -1097,10 +1134,10 @@ int launch_swin_fused(FusedBlockParams p, int num_sms, cudaStream_t stream) {
     SWN_CUDA(cudaGetLastError());
     return 0;
   };
-  if (C == 12 && p.nH == 3) return go(swin_fused_kernel<12, 3, 256, 3>);
-  if (C == 24 && p.nH == 3) return go(swin_fused_kernel<24, 3, 256, 2>);
-  if (C == 48 && p.nH == 3) return go(swin_fused_kernel<48, 3, 512, 1>);
-  if (C == 48 && p.nH == 6) return go(swin_fused_kernel<48, 6, 512, 1>);
+  if (C == 12 && p.nH == 3) return p.phase_cycles ? go(swin_fused_kernel<12, 3, 256, 3, true>) : go(swin_fused_kernel<12, 3, 256, 3, false>);
+  if (C == 24 && p.nH == 3) return p.phase_cycles ? go(swin_fused_kernel<24, 3, 256, 2, true>) : go(swin_fused_kernel<24, 3, 256, 2, false>);
+  if (C == 48 && p.nH == 3) return p.phase_cycles ? go(swin_fused_kernel<48, 3, 512, 1, true>) : go(swin_fused_kernel<48, 3, 512, 1, false>);
+  if (C == 48 && p.nH == 6) return p.phase_cycles ? go(swin_fused_kernel<48, 6, 512, 1, true>) : go(swin_fused_kernel<48, 6, 512, 1, false>);
   SWN_CHECK(false, "swin_fused: no kernel instance for C=%d nH=%d (built: 12/3, 24/3, 48/3, 48/6)", C, p.nH);
   return 1;
 }

@@ -16,6 +16,7 @@ ap.add_argument("--heads", type=int, default=3)
 ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--H", type=int, default=125)
 ap.add_argument("--W", type=int, default=240)
+ap.add_argument("--attn-only", action="store_true")
 a = ap.parse_args()
 C, nH, B, H, W = a.C, a.heads, a.batch, a.H, a.W
 M = B * H * W
@@ -30,8 +31,10 @@ if C == 96:
              "proj: MMA issue", "proj: issue loads", "proj: MMA wait"]
 else:
     Wpk, fpk = packing.pack_fused_block(*params, nH)
-    do_mlp = True
-    names = [f"phase {i}" for i in range(16)]
+    do_mlp = not a.attn_only
+    names = ["write-back(prev)+tok", "loads landed", "LN1 stats", "LN1 normalise", "qkv MMA", "qkv epilogue", "attention",
+             "proj MMA", "proj epilogue", "LN2", "fc1 MMA", "GELU (batched)", "hidden-tile wait", "GELU (chunk)", "fc2 MMA",
+             "final epilogue"]
 for _ in range(2):
     ops.swin_block_fused(x, out, B, H, W, C, nH, 1e-5, Wpk, fpk, do_mlp)
 buf = torch.zeros(148 * 4, 16, dtype=torch.int64, device="cuda")
