@@ -181,6 +181,149 @@ __global__ void __launch_bounds__(128) conv_head_kernel(const float* __restrict_
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tensor-core form of the same head tail (implicit GEMM on mma.sync m16n8k8 TF32, fp32 accumulate): M = pixels,
+// K = 9 taps x CI (taps padded to whole k8 steps), N = CM.  Persistent CTAs stage the tap-major weights once (rounded
+// to TF32), then loop over 8 x 32 pixel tiles: the (8+2) x (32+2) x CI input halo is staged in shared memory (rounded to
+// TF32 once, pixel stride padded so that the A-fragment loads are bank-conflict free), each warp owns one tile row
+// (two m16 tiles); epilogue = +bias, exact-erf GELU, the 1x1 conv as per-lane partial dot products reduced over the
+// four lanes that share a pixel, cropped NCHW store.  TF32 keeps 10 mantissa bits of the operands (error ~1e-4 of the
+// output scale, 200x inside the 2e-2 gate); the fp32 CUDA-core kernel above stays as the exact variant.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void mma_tf32(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int CI, int CM>
+__global__ void __launch_bounds__(256) conv_head_mma_kernel(const float* __restrict__ tok, const float* __restrict__ w1,
+                                                            const float* __restrict__ b1, const float* __restrict__ w2,
+                                                            const float* __restrict__ b2, float* __restrict__ out, int B,
+                                                            int Hh, int Wh, int Cout, int Hout, int Wout) {
+  constexpr int TH = 8, TW = 32;
+  constexpr int CIP = (CI % 32 == 16) ? CI + 4 : CI;      // pixel stride (floats): conflict-free fragment loads
+  constexpr int KST = (CI + 7) / 8;                       // k8 steps per tap
+  constexpr int NT = (CM + 7) / 8;                        // n8 tiles
+  constexpr int CMP = 24;                                 // weight row stride (floats): conflict-free B loads
+  static_assert(CI % 4 == 0 && CM <= CMP && CM % 2 == 0, "unsupported head shape");
+  extern __shared__ __align__(16) float cm_s[];
+  float* w_s = cm_s;                                      // [9][KST][8][CMP]
+  float* in_s = w_s + 9 * KST * 8 * CMP;                  // [(TH+2)*(TW+2)][CIP] (+8 floats slack for the k padding)
+  float* b1_s = in_s + (TH + 2) * (TW + 2) * CIP + 8;     // [NT*8]
+  float* w2_s = b1_s + NT * 8;                            // [2][NT*8]
+  float* b2_s = w2_s + 2 * NT * 8;                        // [2]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+  for (int i = tid; i < 9 * KST * 8 * CMP; i += 256) {
+    const int n = i % CMP, k = (i / CMP) % 8, ks = (i / (CMP * 8)) % KST, tap = i / (CMP * 8 * KST);
+    const int ci = ks * 8 + k;
+    w_s[i] = (n < CM && ci < CI) ? to_tf32(w1[(n * CI + ci) * 9 + tap]) : 0.f;     // w1 is [CM][CI][3][3]
+  }
+  for (int i = tid; i < NT * 8; i += 256) {
+    b1_s[i] = i < CM ? b1[i] : 0.f;
+    w2_s[i] = i < CM ? w2[i] : 0.f;
+    w2_s[NT * 8 + i] = (i < CM && Cout > 1) ? w2[CM + i] : 0.f;
+  }
+  if (tid < 2) b2_s[tid] = tid < Cout ? b2[tid] : 0.f;
+  if (tid < 8) in_s[(TH + 2) * (TW + 2) * CIP + tid] = 0.f;
+  const int tiles_x = (Wout + TW - 1) / TW, tiles_y = (Hout + TH - 1) / TH;
+  const long long n_tiles = (long long)B * tiles_y * tiles_x;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int b = (int)(tile / (tiles_y * tiles_x));
+    const int tr = (int)(tile - (long long)b * tiles_y * tiles_x);
+    const int y0 = (tr / tiles_x) * TH, x0 = (tr % tiles_x) * TW;
+    __syncthreads();   // previous tile fully consumed (and the weights staged, first time round)
+    for (int i = tid; i < (TH + 2) * (TW + 2) * (CI / 4); i += 256) {
+      const int c4 = i % (CI / 4), pix = i / (CI / 4);
+      const int yy = y0 - 1 + pix / (TW + 2), xx = x0 - 1 + pix % (TW + 2);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (yy >= 0 && yy < Hh && xx >= 0 && xx < Wh) v = __ldg(reinterpret_cast<const float4*>(tok + (((long long)b * Hh + yy) * Wh + xx) * CI + c4 * 4));
+      *reinterpret_cast<float4*>(in_s + pix * CIP + c4 * 4) = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+    }
+    __syncthreads();
+    float acc[2][NT][4];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int n = 0; n < NT; ++n) acc[m][n][0] = acc[m][n][1] = acc[m][n][2] = acc[m][n][3] = 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const float* arow = in_s + ((warp + tap / 3) * (TW + 2) + tap % 3 + g) * CIP + t4;
+      const float* wt = w_s + tap * KST * 8 * CMP + t4 * CMP + g;
+#pragma unroll
+      for (int ks = 0; ks < KST; ++ks) {
+        uint32_t a[2][4];
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          const float* ap = arow + m * 16 * CIP + ks * 8;
+          a[m][0] = __float_as_uint(ap[0]);
+          a[m][1] = __float_as_uint(ap[8 * CIP]);
+          a[m][2] = __float_as_uint(ap[4]);
+          a[m][3] = __float_as_uint(ap[8 * CIP + 4]);
+        }
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+          const uint32_t b0 = __float_as_uint(wt[ks * 8 * CMP + n * 8]), b1v = __float_as_uint(wt[(ks * 8 + 4) * CMP + n * 8]);
+          mma_tf32(acc[0][n], a[0], b0, b1v);
+          mma_tf32(acc[1][n], a[1], b0, b1v);
+        }
+      }
+    }
+    // epilogue: accumulator (row g | g+8 = pixel, col 2*t4 | 2*t4+1 = channel)
+    const int y = y0 + warp;
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      float o[2][2] = {{0.f, 0.f}, {0.f, 0.f}};   // [pixel half][cout]
+#pragma unroll
+      for (int n = 0; n < NT; ++n)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int ch = n * 8 + 2 * t4 + (e & 1);
+          const float av = acc[m][n][e] + b1_s[ch];
+          const float h = gelu_erf(av);     // A&S 7.1.26 erf, |err| <= 1.5e-7: exact at fp32 output precision
+          o[e >> 1][0] = fmaf(h, w2_s[ch], o[e >> 1][0]);
+          o[e >> 1][1] = fmaf(h, w2_s[NT * 8 + ch], o[e >> 1][1]);
+        }
+#pragma unroll
+      for (int hlf = 0; hlf < 2; ++hlf)
+#pragma unroll
+        for (int co = 0; co < 2; ++co) {
+          float r = o[hlf][co];
+          r += __shfl_xor_sync(0xffffffffu, r, 1);
+          r += __shfl_xor_sync(0xffffffffu, r, 2);
+          const int x = x0 + m * 16 + hlf * 8 + g;
+          if (t4 == 0 && co < Cout && y < Hout && x < Wout) out[(((long long)b * Cout + co) * Hout + y) * Wout + x] = r + b2_s[co];
+        }
+    }
+  }
+}
+
+template <int CI, int CM>
+static int launch_conv_head_mma(const float* tok, const float* w1, const float* b1, const float* w2, const float* b2, float* out,
+                                int B, int Hh, int Wh, int Cout, int Hout, int Wout, int ctas_per_sm, cudaStream_t st) {
+  constexpr int CIP = (CI % 32 == 16) ? CI + 4 : CI, KST = (CI + 7) / 8, NT = (CM + 7) / 8;
+  const size_t smem = (size_t)(9 * KST * 8 * 24 + 10 * 34 * CIP + 8 + NT * 8 * 3 + 2) * sizeof(float);
+  SWN_CUDA(cudaFuncSetAttribute(conv_head_mma_kernel<CI, CM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long n_tiles = (long long)B * ((Hout + 7) / 8) * ((Wout + 31) / 32);
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  long long grid = (long long)sms * ctas_per_sm;
+  if (grid > n_tiles) grid = n_tiles;
+  conv_head_mma_kernel<CI, CM><<<(unsigned)grid, 256, smem, st>>>(tok, w1, b1, w2, b2, out, B, Hh, Wh, Cout, Hout, Wout);
+  SWN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+#ifndef SWN_HEAD_TF32
+#define SWN_HEAD_TF32 1
+#endif
+constexpr bool HEAD_TF32 = SWN_HEAD_TF32 != 0;   // 0: exact fp32 CUDA-core heads
+
 // bilinear upsample (align_corners=False, integer scale) of [B,Hq,Wq] to [B,Hout,Wout] (cropped)
 __global__ void bilinear_up_kernel(const float* __restrict__ lo, float* __restrict__ out, int B, int Hq, int Wq, int up,
                                    int Hout, int Wout) {
@@ -205,11 +348,16 @@ int launch_seg_head(const float* tok, const float* w1, const float* b1, const fl
                     float* out, int B, int Hq, int Wq, int up, int Hout, int Wout, cudaStream_t st) {
   constexpr int CI = 48, CM = 24;
   const size_t smem = (size_t)(9 * CI * CM + CM + 2 * CM + 2) * sizeof(float);
-  constexpr int PX = 4;
-  SWN_CUDA(cudaFuncSetAttribute(conv_head_kernel<CI, CM, PX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const long long n_lo = (long long)B * Hq * ((Wq + PX - 1) / PX);
-  conv_head_kernel<CI, CM, PX><<<(unsigned)((n_lo + 127) / 128), 128, smem, st>>>(tok, w1, b1, w2, b2, lowres, B, Hq, Wq, 1, Hq, Wq);
-  SWN_CUDA(cudaGetLastError());
+  if (HEAD_TF32) {
+    const int rc = launch_conv_head_mma<CI, CM>(tok, w1, b1, w2, b2, lowres, B, Hq, Wq, 1, Hq, Wq, 2, st);
+    if (rc) return rc;
+  } else {
+    constexpr int PX = 4;
+    SWN_CUDA(cudaFuncSetAttribute(conv_head_kernel<CI, CM, PX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long n_lo = (long long)B * Hq * ((Wq + PX - 1) / PX);
+    conv_head_kernel<CI, CM, PX><<<(unsigned)((n_lo + 127) / 128), 128, smem, st>>>(tok, w1, b1, w2, b2, lowres, B, Hq, Wq, 1, Hq, Wq);
+    SWN_CUDA(cudaGetLastError());
+  }
   const long long n_hi = (long long)B * Hout * Wout;
   bilinear_up_kernel<<<(unsigned)((n_hi + 255) / 256), 256, 0, st>>>(lowres, out, B, Hq, Wq, up, Hout, Wout);
   SWN_CUDA(cudaGetLastError());
@@ -222,6 +370,7 @@ int launch_recon_head(const float* tok, const float* w1, const float* b1, const 
   SWN_CHECK(Cout >= 1 && Cout <= 2, "recon_head: Cout must be 1 or 2");
   SWN_CHECK(Hout <= Hh && Wout <= Wh, "recon_head: crop larger than source");
   const size_t smem = (size_t)(9 * CI * CM + CM + 2 * CM + 2) * sizeof(float);
+  if (HEAD_TF32) return launch_conv_head_mma<CI, CM>(tok, w1, b1, w2, b2, out, B, Hh, Wh, Cout, Hout, Wout, 4, st);
   constexpr int PX = 4;
   const long long n = (long long)B * Hout * ((Wout + PX - 1) / PX);
   conv_head_kernel<CI, CM, PX><<<(unsigned)((n + 127) / 128), 128, smem, st>>>(tok, w1, b1, w2, b2, out, B, Hh, Wh, Cout, Hout, Wout);

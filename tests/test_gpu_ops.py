@@ -14,6 +14,7 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 TOL_BF16 = 2e-2
 TOL_F32 = 1e-4
+TOL_HEAD = 2e-3   # conv heads: TF32 tensor-core operands (10-bit mantissa), fp32 accumulation
 OPD = S.ops.operand_dtype()   # 16-bit tensor-core operand dtype of the built library (fp16 default)
 
 
@@ -214,7 +215,7 @@ def test_segmentation_head(scale):
     with torch.no_grad():
         out = m(x.to(DEV), res, scale_factor=scale)
     torch.cuda.synchronize()
-    assert relerr(out, ref) <= TOL_F32
+    assert relerr(out, ref) <= TOL_HEAD
 
 
 def test_recon_head_and_glue():
@@ -227,12 +228,12 @@ def test_recon_head_and_glue():
     out = torch.empty(B, 2, 10, 18, device=DEV)
     ops.recon_head(x.to(DEV), w1.to(DEV), b1.to(DEV), w2.to(DEV), b2.to(DEV), out, B, H, W, 2, 10, 18)
     torch.cuda.synchronize()
-    assert relerr(out, ref) <= TOL_F32
+    assert relerr(out, ref) <= TOL_HEAD
     full = (h @ w2.view(2, 12).t() + b2).permute(0, 3, 1, 2)            # uncropped, row length a multiple of 4
     out4 = torch.empty(B, 2, H, W, device=DEV)
     ops.recon_head(x.to(DEV), w1.to(DEV), b1.to(DEV), w2.to(DEV), b2.to(DEV), out4, B, H, W, 2, H, W)
     torch.cuda.synchronize()
-    assert relerr(out4, full) <= TOL_F32
+    assert relerr(out4, full) <= TOL_HEAD
     # glue: ensure_2ch + sigmoid mask + minmax + normalize / denormalize round trip
     img = rnd(B, 1, H, W, seed=6).abs() * 100 + 5
     seg = rnd(B, 1, H, W, seed=7)
