@@ -42,7 +42,7 @@ def peaks():
 
 # dram__bytes_read.sum + dram__bytes_write.sum per step of the kernel family, summed over its launches, from the
 # `ncu --set full` captures summarised under profiles/ (null = not captured for this build)
-TRAFFIC_NCU = {"fused": None, "mlp": None}
+TRAFFIC_NCU = {"fused": 22.7e9, "mlp": None}   # bytes per step (22 launches at batch 64), profiles/r1_ncu_fused_*.txt
 
 
 def shard_bounds(n_items, rank, world):

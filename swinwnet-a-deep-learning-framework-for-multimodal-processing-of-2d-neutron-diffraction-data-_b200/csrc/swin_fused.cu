@@ -906,7 +906,7 @@ __global__ void __launch_bounds__(512, 1) swin_attn_stream_kernel(const FusedBlo
 #pragma unroll
       for (int t = 0; t < 4; ++t, ++n_use) {
         const int wslot = n_use & 3;
-        mbar_wait(&bars->full[wslot], (n_use >> 2) & 1u);
+        mbar_wait_spin(&bars->full[wslot], (n_use >> 2) & 1u);
         tc_fence_after();
         if (elect_one()) {
           const int ch = t >> 1, kb = t & 1;
@@ -964,7 +964,7 @@ __global__ void __launch_bounds__(512, 1) swin_attn_stream_kernel(const FusedBlo
 #pragma unroll
       for (int kb = 0; kb < 2; ++kb, ++n_use) {
         const int wslot = n_use & 3;
-        mbar_wait(&bars->full[wslot], (n_use >> 2) & 1u);
+        mbar_wait_spin(&bars->full[wslot], (n_use >> 2) & 1u);
         tc_fence_after();
         if (elect_one()) {
           const uint64_t bd0 = umma_desc_sw128(smem_u32(ring + wslot * FS_STAGE));
