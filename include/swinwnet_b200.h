@@ -112,6 +112,13 @@ int swn_copy_cols(const float* src, int lds, float* dst, int ldd, long long rows
 int swn_sigmoid_mask(const float* img, int Cimg, const float* seg, float* images2, float* seg_map, float* masked,
                      float* minmax, int B, int Cout, int H, int W, void* stream);
 
+/* d-space front end of the physics metrics (Qwrapper.tensor_to_d, Diffraction_metrics.py:35-70), whole batch in one
+ * launch: out[b, bin] = sum over pixels p with bin_of_pixel[p] == bin of img[b * img_stride + p] (channel 0 of image b;
+ * img_stride in floats).  bin_of_pixel = int32 [n_pixels], -1 = pixel dropped (d > 7.5); built once per geometry by
+ * physics.py with the reference's own fp32 bucketize.  out [B, n_bins] fp32 is zeroed by the call. */
+int swn_dspace_histogram(const float* img, long long img_stride, const int* bin_of_pixel, int B, int n_pixels, int n_bins,
+                         float* out, void* stream);
+
 /* normalize_piecewise (inverse=0) / denormalize_piecewise (inverse=1) (ST_Inference_Pipline.py:39-67). */
 int swn_normalize(const float* x, const float* minmax, float* out, int BC, int H, int W, float threshold, float eps,
                   int inverse, void* stream);

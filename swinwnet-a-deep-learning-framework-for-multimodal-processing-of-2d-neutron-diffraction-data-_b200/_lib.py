@@ -47,6 +47,7 @@ SIGNATURES = {
     "swn_copy_cols": (c_int, [c_void_p, c_int, c_void_p, c_int, c_longlong, c_int, c_void_p]),
     "swn_sigmoid_mask": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                  c_int, c_void_p]),
+    "swn_dspace_histogram": (c_int, [c_void_p, c_longlong, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "swn_normalize": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_int, c_void_p]),
 }
 

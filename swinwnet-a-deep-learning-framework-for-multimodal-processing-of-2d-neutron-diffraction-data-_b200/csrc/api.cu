@@ -158,6 +158,12 @@ int swn_sigmoid_mask(const float* img, int Cimg, const float* seg, float* images
                              reinterpret_cast<cudaStream_t>(stream));
 }
 
+int swn_dspace_histogram(const float* img, long long img_stride, const int* bin_of_pixel, int B, int n_pixels, int n_bins,
+                         float* out, void* stream) {
+  SWN_CHECK(img && bin_of_pixel && out, "dspace_histogram: null pointer");
+  return launch_dspace_hist(img, img_stride, bin_of_pixel, B, n_pixels, n_bins, out, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int swn_normalize(const float* x, const float* minmax, float* out, int BC, int H, int W, float threshold, float eps,
                   int inverse, void* stream) {
   SWN_CHECK(x && minmax && out, "normalize: null pointer");

@@ -496,4 +496,43 @@ int launch_normalize(const float* x, const float* minmax, float* out, int BC, in
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// d-space front end of the physics metrics (Qwrapper.tensor_to_d, Diffraction_metrics.py:35-70): I(d)[b, bin] = sum of
+// channel 0 of image b over the pixels whose d = L / (2 sin(|theta|/2)) falls into the bin.  The pixel -> bin map
+// depends only on (H, W, centers); it is computed once on the host with the reference's own fp32 bucketize (so that
+// pixels on bin edges fall exactly where the reference puts them; -1 = d > 7.5, dropped) and the whole batch is
+// reduced by ONE launch: a CTA accumulates a slice of one image in a shared-memory histogram and flushes it with
+// global atomics.  (The reference loops over the batch in Python with a device->host copy per sample.)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dspace_hist_kernel(const float* __restrict__ img, long long img_stride,
+                                                          const int* __restrict__ bin_of_pixel, int n_pix, int n_bins,
+                                                          float* __restrict__ out) {
+  extern __shared__ float hist_s[];
+  for (int i = threadIdx.x; i < n_bins; i += blockDim.x) hist_s[i] = 0.f;
+  __syncthreads();
+  const float* src = img + (long long)blockIdx.y * img_stride;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pix; i += gridDim.x * blockDim.x) {
+    const int bin = bin_of_pixel[i];
+    if (bin >= 0) atomicAdd(&hist_s[bin], src[i]);
+  }
+  __syncthreads();
+  float* dst = out + (long long)blockIdx.y * n_bins;
+  for (int i = threadIdx.x; i < n_bins; i += blockDim.x) {
+    const float v = hist_s[i];
+    if (v != 0.f) atomicAdd(&dst[i], v);
+  }
+}
+
+int launch_dspace_hist(const float* img, long long img_stride, const int* bin_of_pixel, int B, int n_pix, int n_bins,
+                       float* out, cudaStream_t st) {
+  SWN_CHECK(B > 0 && n_pix > 0 && n_bins > 0 && n_bins <= 12000, "dspace_hist: bad sizes (B=%d pixels=%d bins=%d)", B, n_pix, n_bins);
+  SWN_CUDA(cudaMemsetAsync(out, 0, (size_t)B * n_bins * sizeof(float), st));
+  int slices = (n_pix + 256 * 64 - 1) / (256 * 64);     // ~64 pixels per thread
+  if (slices < 1) slices = 1;
+  dspace_hist_kernel<<<dim3((unsigned)slices, (unsigned)B), 256, (size_t)n_bins * sizeof(float), st>>>(img, img_stride, bin_of_pixel, n_pix,
+                                                                                                        n_bins, out);
+  SWN_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace swn

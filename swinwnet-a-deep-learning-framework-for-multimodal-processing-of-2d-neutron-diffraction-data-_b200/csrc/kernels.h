@@ -120,6 +120,8 @@ int launch_recon_head(const float* tok, const float* w1, const float* b1, const 
 int launch_copy_cols(const float* src, int lds, float* dst, int ldd, long long rows, int cols, cudaStream_t s);
 int launch_sigmoid_mask(const float* img, int Cimg, const float* seg, float* images2, float* seg_map, float* masked,
                         float* minmax, int B, int Cout, int H, int W, cudaStream_t s);
+int launch_dspace_hist(const float* img, long long img_stride, const int* bin_of_pixel, int B, int n_pix, int n_bins,
+                       float* out, cudaStream_t s);
 int launch_normalize(const float* x, const float* minmax, float* out, int BC, int H, int W, float thr, float eps,
                      int inverse, cudaStream_t s);
 

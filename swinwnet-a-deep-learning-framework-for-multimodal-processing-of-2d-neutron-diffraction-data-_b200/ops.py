@@ -18,7 +18,7 @@ def operand_dtype():
 LAUNCH_COUNT = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
 _LAUNCHES_PER_CALL = {"swin_block_small": 1, "swin_block_fused": 1, "rowgemm": 1,"mlp": 1, "window_attention": 1, "cross_attention": 1, "patch_embed": 1,
                       "seg_head": 2, "recon_head": 1, "copy_cols": 1, "sigmoid_mask": 1, "sigmoid_mask_mm": 2,
-                      "normalize": 1}
+                      "normalize": 1, "dspace_histogram": 2}
 
 
 def _count(kind):
@@ -159,4 +159,16 @@ def normalize(x, minmax, inverse, threshold=0.01, eps=1e-6):
     _lib.check(_lib.load().swn_normalize(_ptr(x), _ptr(minmax), _ptr(out), B * C, H, W, threshold, eps, int(inverse),
                                          _stream()), "swn_normalize")
     _count("normalize")
+    return out
+
+
+def dspace_histogram(img, bin_of_pixel, n_bins):
+    """img [B, C, H, W] fp32 CUDA (channel 0 is used), bin_of_pixel int32 [H*W] -> [B, n_bins] fp32 (one launch)."""
+    _need_cuda(img, bin_of_pixel)
+    B, C, H, W = img.shape
+    img = img.float().contiguous()
+    out = torch.empty(B, n_bins, device=img.device, dtype=torch.float32)
+    _lib.check(_lib.load().swn_dspace_histogram(_ptr(img), C * H * W, _ptr(bin_of_pixel), B, H * W, n_bins, _ptr(out), _stream()),
+               "swn_dspace_histogram")
+    _count("dspace_histogram")
     return out

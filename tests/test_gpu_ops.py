@@ -332,6 +332,23 @@ def test_swin_attn_stream_c96(nH, B, H, W):
     assert relerr(out, ref) <= TOL_BF16 / 4
 
 
+def test_dspace_histogram_matches_oracle():
+    """physics front end: batched I(d) histogram kernel against the oracle's restatement of
+    Qwrapper.tensor_to_d, HR and LR geometries of the reference protocol (tests.py:168-172)."""
+    import numpy as np
+    from oracle import diffraction_metrics_oracle as DM
+    from swinwnet_b200 import physics
+    for (H, W, centers) in ((500, 960, DM.D_CENTERS_HR), (250, 480, DM.D_CENTERS_LR)):
+        x = rnd(3, 2, H, W, seed=H).abs() * 100 + 1
+        q = physics.Qwrapper(fixed_centers=centers, device=DEV)
+        res = q.tensor_to_d(x.to(DEV))
+        assert len(res) == 3 and res[0]["d"].shape == (len(centers),)
+        for b in range(3):
+            d_ref, I_ref = DM.to_d_space(x[b, 0].numpy(), centers)
+            assert np.allclose(res[b]["d"], d_ref)
+            assert np.abs(res[b]["I"] - I_ref).max() <= 1e-5 * np.abs(I_ref).max()
+
+
 def test_copy_cols():
     src = rnd(37, 48, seed=1).to(DEV)
     dst = torch.zeros(37, 96, device=DEV)

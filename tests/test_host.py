@@ -128,3 +128,31 @@ def test_gelu_fast_formula_against_exact_erf_gelu():
     g = 0.5 * x * (1.0 + np.tanh(x * (a0 + x2 * (a1 + x2 * a2))))
     ref = 0.5 * x * (1.0 + np.vectorize(math.erf)(x / math.sqrt(2.0)))
     assert np.abs(g - ref).max() <= 3.2e-5
+
+
+def test_checkpoint_ingestion_variants():
+    """nested / DataParallel-prefixed checkpoints of either depth configuration load strict=True, with
+    depths and modality inferred from the keys (reference viewer: inference_gui/swinwnet_viewer_gui.py:129-151)."""
+    import json
+    import os
+    import torch
+    import swinwnet_b200 as S
+    import benchdata
+    man = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "manifest.json")))
+    from swinwnet_b200 import checkpoint as ck
+    sd = benchdata.make_state_dict(man["wnet_em"], seed=5)
+    wrapped = {"epoch": 3, "model_state_dict": {"module." + k: v for k, v in sd.items()}}
+    got = ck.load_state_dict_any(wrapped)
+    assert set(got) == set(sd) and ck.infer_error_matrix_flag_from_sd(got)
+    assert ck.infer_depths_from_sd(got) == [2, 2, 2, 2]
+    m = ck.build_model_from_checkpoint(wrapped)
+    assert isinstance(m, S.SwinWNet) and all(torch.equal(v, sd[k]) for k, v in m.state_dict().items())
+    sd6 = benchdata.make_state_dict(man["wnet_em_default_depths"], seed=6)
+    assert ck.infer_depths_from_sd(sd6) == [2, 2, 6, 2]
+    assert isinstance(ck.build_model_from_checkpoint({"state_dict": sd6}), S.SwinWNet)
+    assert not ck.infer_error_matrix_flag_from_sd(benchdata.make_state_dict(man["wnet"], seed=7))
+    assert isinstance(ck.build_model_from_checkpoint(benchdata.make_state_dict(man["unet"], seed=8)), S.SwinUNet)
+    assert isinstance(ck.build_model_from_checkpoint(benchdata.make_state_dict(man["unetsr"], seed=9)), S.SwinUNetSR)
+    import pytest
+    with pytest.raises(ValueError):
+        ck.load_state_dict_any([1, 2, 3])
