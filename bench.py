@@ -211,10 +211,14 @@ def main():
     def step_dev():
         inf(x_dev)
 
+    # one chunk per step: the H2D of step i+1 and the D2H of step i then overlap the compute of their neighbours across
+    # steps (copy streams), all inside the timed region; smaller chunks also overlap inside a step but run the deep,
+    # narrow layers of the net on half-filled waves
+    E2E_CHUNK = int(os.environ.get("SWN_E2E_CHUNK", B))
+
     def step_e2e():
-        xd = x_host.to(dev, non_blocking=True)
-        out = inf(xd)
-        out_host.copy_(out, non_blocking=True)
+        # public host-data call: pinned host inputs -> pinned host result, copies pipelined against compute in chunks
+        inf.run_host(x_host, out=out_host, chunk=E2E_CHUNK)
 
     for _ in range(W_):
         step_dev()

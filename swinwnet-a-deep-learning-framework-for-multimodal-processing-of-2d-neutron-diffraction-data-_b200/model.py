@@ -27,7 +27,9 @@ import torch.nn as nn
 from . import ops, packing
 
 WINDOW = 5
-FUSED_BLOCK = True   # route C <= 64 shift-0 blocks through the single-kernel path (csrc/swin_fused.cu)
+FUSED_BLOCK = True   # route shift-0 blocks of the widths below through the single-kernel paths (csrc/swin_fused.cu)
+FUSED_WHOLE = {(12, 3), (24, 3), (48, 3), (48, 6)}    # (C, heads) instances of swin_fused_kernel (whole block)
+FUSED_ATTN = {(96, 3), (96, 6)}                       # instances of swin_attn_stream_kernel (attention half)
 
 
 def _check_infer(x):
@@ -168,7 +170,7 @@ class SwinTransformerBlock(nn.Module):
         B, L, C = x.shape
         H, W = resolution
         assert L == H * W, "input feature has wrong size"
-        if FUSED_BLOCK and C <= 48 and self.shift_size == 0 and x.data_ptr() != out.data_ptr():
+        if FUSED_BLOCK and (C, self.num_heads) in FUSED_WHOLE and self.shift_size == 0 and x.data_ptr() != out.data_ptr():
             # narrow layers (C = 12 / 24 / 48): the whole block is one tcgen05 kernel (csrc/swin_fused.cu)
             Wpk, fpk = self._packed_fused()
             ops.swin_block_fused(x, out, B, H, W, C, self.num_heads, self.norm1.eps, Wpk, fpk, True)
@@ -185,7 +187,7 @@ class SwinTransformerBlock(nn.Module):
             return out
         pk = self._packed()
         M = B * L
-        if FUSED_BLOCK and C == 96 and self.num_heads in (3, 6) and self.shift_size == 0:
+        if FUSED_BLOCK and (C, self.num_heads) in FUSED_ATTN and self.shift_size == 0:
             # attention half as one streamed-weight tcgen05 kernel (csrc/swin_fused.cu), MLP half as before
             if tmp is None:
                 tmp = torch.empty_like(out)
@@ -226,7 +228,7 @@ class BasicLayer(nn.Module):
 
     def run(self, x, resolution, inplace=False):
         """returns the layer output; with inplace=True the caller gives up x (it may be overwritten or returned)."""
-        if FUSED_BLOCK and x.shape[-1] <= 48 and all(b.shift_size == 0 for b in self.blocks):
+        if FUSED_BLOCK and all((b.dim, b.num_heads) in FUSED_WHOLE and b.shift_size == 0 for b in self.blocks):
             # single-kernel blocks never run in place: ping-pong between two buffers
             spare = None
             for i, blk in enumerate(self.blocks):

@@ -14,6 +14,8 @@ class SwinWNetInference:
         self.device = device
         self.model.eval()
         self.max_batch = max_batch
+        self._copy_streams = None
+        self.host_done = None          # CUDA event: the last run_host() result has landed in host memory
         self._reset_outputs()
 
     _STAGES = ("images", "seg_map_lr", "images_masked_lr", "norm", "upscaled_norm", "upscaled_denorm", "seg_map_hr",
@@ -60,3 +62,45 @@ class SwinWNetInference:
             for k, v in out.items():
                 setattr(self, k, v)
         return self.images_masked_hr
+
+    def run_host(self, images, out=None, chunk=32, two_channel=True):
+        """End-to-end call for HOST data: ``images`` [B,1|2,H,W] fp32 in (ideally pinned) host memory -> ``out``
+        [B,Cout,2H,2W] fp32 pinned host tensor holding ``images_masked_hr``.  The batch is cut into chunks; the H2D copy of
+        chunk i+1 and the D2H copy of chunk i-1 run on two copy streams while chunk i computes on the current stream, so
+        only the first input chunk and the last output chunk are exposed.  Returns ``out`` immediately; the data is valid
+        after ``self.host_done.synchronize()`` (or any device-wide synchronisation).  The cached stage attributes are
+        those of the last chunk."""
+        dev = torch.device(self.device)
+        if self._copy_streams is None:
+            self._copy_streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        h2d, d2h = self._copy_streams
+        main = torch.cuda.current_stream(dev)
+        B, Cin, H, W = images.shape
+        cout = 2 if (two_channel or Cin == 2) else Cin
+        if out is None:
+            out = torch.empty(B, cout, 2 * H, 2 * W, dtype=torch.float32).pin_memory()
+        h2d.wait_stream(main)            # the caller may still be producing `images` / consuming device buffers
+        self._reset_outputs()
+        with torch.no_grad():
+            staged = []
+            for lo in range(0, B, chunk):      # all input copies are queued up front (0.96 MB per diffraction)
+                with torch.cuda.stream(h2d):
+                    xd = images[lo:lo + chunk].to(dev, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(h2d)
+                staged.append((lo, xd, ev))
+            for lo, xd, ev in staged:
+                main.wait_event(ev)
+                xd.record_stream(main)
+                res = self._run(xd, two_channel)
+                done = torch.cuda.Event()
+                done.record(main)
+                with torch.cuda.stream(d2h):
+                    d2h.wait_event(done)
+                    out[lo:lo + xd.shape[0]].copy_(res["images_masked_hr"], non_blocking=True)
+                res["images_masked_hr"].record_stream(d2h)
+            for k, v in res.items():
+                setattr(self, k, v)
+            self.host_done = torch.cuda.Event()
+            self.host_done.record(d2h)
+        return out

@@ -132,6 +132,20 @@ def test_batch_independence_and_determinism_full_size(wnet_em):
     assert full.shape == (3, 2, 500, 960) and torch.isfinite(full).all()
 
 
+def test_run_host_pipelined_copies_match_device_call(wnet_em):
+    """public host-data call (pinned host in -> pinned host out, chunked, copies overlapped with compute on side streams)
+    returns exactly what the device call returns, chunk boundaries and ragged last chunk included."""
+    x = O.synthetic_diffractions(5, seed=33, H=60, W=80, two_channel=False)
+    inf = S.SwinWNetInference(wnet_em, DEV)
+    ref = inf(x.to(DEV)).clone()
+    xh = x.pin_memory()
+    for chunk in (2, 5, 8):
+        out = inf.run_host(xh, chunk=chunk)
+        inf.host_done.synchronize()
+        assert out.is_pinned() and out.shape == ref.shape
+        assert torch.equal(out, ref.cpu())
+
+
 def test_state_dict_round_trip_and_repack(manifest):
     sd = O.make_state_dict(manifest["unet"], seed=2)
     m = S.SwinUNet(depths=D2)
