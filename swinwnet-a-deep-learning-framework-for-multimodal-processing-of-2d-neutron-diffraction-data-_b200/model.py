@@ -131,7 +131,9 @@ class SwinTransformerBlock(nn.Module):
             if self.window_size != WINDOW or int(C * self.mlp_ratio) != 4 * C:
                 raise NotImplementedError("swinwnet_b200: kernels are built for window_size=5, mlp_ratio=4")
             d = {}
-            nv = packing.choose_chunk(3 * C, 256)
+            # N-chunk of the qkv GEMM: at K = 192 the weight tiles of a 192-column chunk (24 KB) leave room for only two ring
+            # stages next to the resident A tile; 96-column chunks (5 stages) measured 20 % faster (0.63 -> 0.51 ms)
+            nv = packing.choose_chunk(3 * C, 128 if C <= 192 else 256)
             d["qkv"] = packing.pack_rowgemm(a.qkv.weight, a.qkv.bias, nv) + (nv,)
             nv = packing.choose_chunk(C, 256)
             d["proj"] = packing.pack_rowgemm(a.proj.weight, a.proj.bias, nv) + (nv,)

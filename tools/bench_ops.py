@@ -89,7 +89,7 @@ for (L, C, nH, H, W) in SHAPES:
         report("mlp", M, C, ms, M * C * 8, 16.0 * M * C * C)
     if "qkv" in a.ops:
         Wq, bq = torch.randn(3 * C, C, device=DEV) * C ** -0.5, torch.zeros(3 * C, device=DEV)
-        nv = packing.choose_chunk(3 * C, 256)
+        nv = packing.choose_chunk(3 * C, int(os.environ.get("SWN_QKV_NT", 256)))
         Wp, bp, NT, nch = packing.pack_rowgemm(Wq, bq, nv)
         qkv = torch.empty(M, 3 * C, device=DEV, dtype=OPD)
         ms = timeit(lambda: ops.rowgemm(A=x, a_mode=ops.A_F32_LN, M=M, K=C, lda=C, ln_w=lw, ln_b=lb, Wp=Wp, NT=NT, nchunks=nch,
@@ -104,7 +104,7 @@ for (L, C, nH, H, W) in SHAPES:
     if "proj" in a.ops:
         att = torch.randn(M, C, device=DEV).to(OPD)
         Wo, bo = torch.randn(C, C, device=DEV) * C ** -0.5, torch.zeros(C, device=DEV)
-        nv = packing.choose_chunk(C, 256)
+        nv = packing.choose_chunk(C, int(os.environ.get("SWN_PROJ_NT", 256)))
         Wp, bp, NT, nch = packing.pack_rowgemm(Wo, bo, nv)
         out = x if a.inplace else torch.empty_like(x)
         ms = timeit(lambda: ops.rowgemm(A=att, a_mode=ops.A_BF16, M=M, K=C, lda=C, Wp=Wp, NT=NT, nchunks=nch, n_valid=nv,
