@@ -13,6 +13,9 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,c
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
 
+NVCC_FLAGS += [f for f in os.environ.get("SWN_NVCC_EXTRA", "").split() if f]   # e.g. -DSWN_MLP_PROFILE=1 (profiling builds)
+
+
 def _digest():
     h = hashlib.sha256()
     for f in SOURCES + HEADERS:

@@ -81,6 +81,7 @@ int swn_mlp(const float* x, float* out, int M, int C, const float* ln_w, const f
   p.x = x; p.out = out; p.M = M; p.C = C; p.ln_w = ln_w; p.ln_b = ln_b; p.ln_eps = ln_eps;
   p.Wp = reinterpret_cast<const op_t*>(Wp); p.b1 = b1; p.b2 = b2;
   mlp_config(C, &p.HC, &p.TR);
+  p.phase_cycles = g_phase_cycles;
   if (C <= 96) return launch_mlp_persist(p, num_sms(), reinterpret_cast<cudaStream_t>(stream));
   return launch_mlp(p, reinterpret_cast<cudaStream_t>(stream));
 }

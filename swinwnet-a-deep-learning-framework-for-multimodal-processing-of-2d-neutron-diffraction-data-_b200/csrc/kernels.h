@@ -57,6 +57,7 @@ struct MlpParams {
   int TR;                   // fc2 output rows per weight tile
   int stages, tmem_cols;    // filled in by the launcher
   int row_stride;           // mlp_persist: staging row stride in bytes (filled in by the launcher)
+  long long* phase_cycles;  // optional [16] clock64 sums (profiling aid, see swn_set_phase_profile)
 };
 int launch_mlp(MlpParams p, cudaStream_t stream);
 int launch_mlp_persist(MlpParams p, int num_sms, cudaStream_t stream);  // C <= 96: persistent, TMA-staged

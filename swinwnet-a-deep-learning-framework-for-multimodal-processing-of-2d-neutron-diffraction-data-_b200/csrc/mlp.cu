@@ -15,6 +15,33 @@
 
 namespace swn {
 
+// profiling aid (build with SWN_NVCC_EXTRA=-DSWN_MLP_PROFILE=1, tools/mlp_phase_profile.py): lane 0 of a warp adds the
+// cycles spent in `stmt` to p.phase_cycles[slot]; compiled out of the product build
+#ifndef SWN_MLP_PROFILE
+#define SWN_MLP_PROFILE 0
+#endif
+#if SWN_MLP_PROFILE
+#define MLP_PROF_ADD(slot, t0)                                                                                             \
+  do {                                                                                                                     \
+    if (p.phase_cycles && lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.phase_cycles + (slot)), (unsigned long long)(clock64() - (t0))); \
+  } while (0)
+#define MLP_CLOCK() clock64()
+#define MLP_TIMED(slot, stmt)                                                                         \
+  do {                                                                                                \
+    if (p.phase_cycles) {                                                                             \
+      const long long _t0 = clock64();                                                                \
+      stmt;                                                                                           \
+      if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.phase_cycles + (slot)), (unsigned long long)(clock64() - _t0)); \
+    } else {                                                                                          \
+      stmt;                                                                                           \
+    }                                                                                                 \
+  } while (0)
+#else
+#define MLP_PROF_ADD(slot, t0) do { (void)(t0); } while (0)
+#define MLP_CLOCK() 0ll
+#define MLP_TIMED(slot, stmt) do { stmt; } while (0)
+#endif
+
 constexpr int MLP_WARPS = 10;
 constexpr int MLP_THREADS = MLP_WARPS * 32;
 constexpr int MLP_EPI_THREADS = 256;
@@ -52,6 +79,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(const MlpParams p) 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long m0 = (long long)blockIdx.x * TILE_M;
+  const long long t_cta0 = MLP_CLOCK();
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -108,7 +136,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(const MlpParams p) 
 
   // ===== prologue: LayerNorm(x) -> resident bf16 A tile (all warps) =====
   {
-    constexpr int UNR = KV == 1 ? 4 : 2;
+    constexpr int UNR = KV == 1 ? 4 : (KV == 2 ? 7 : 2);   // rows in flight per warp (measured: 7 helps at C = 192, hurts at C = 384)
     const float* x = p.x;
     const int M = p.M;
     build_a_tile<LPR, KV, UNR, true>(a_smem, C, C16, p.ln_w, p.ln_b, p.ln_eps, warp, MLP_WARPS, lane, [&](int r, int k) {
@@ -119,6 +147,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(const MlpParams p) 
   }
   fence_proxy_async();
   mbar_arrive(&sh->a_ready);
+  if (warp == 1) MLP_PROF_ADD(12, t_cta0);
 
   if (warp == 0) {
     // ===== weight producer: rest of the stream =====
@@ -136,7 +165,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(const MlpParams p) 
     }
   } else if (warp == 1) {
     // ===== MMA issuer: warp-uniform loop, one elected lane issues tcgen05.mma / commit =====
-    mbar_wait(&sh->a_ready, 0);
+    MLP_TIMED(0, mbar_wait(&sh->a_ready, 0));
+    const long long t_mma0 = MLP_CLOCK();
     const uint32_t idesc1 = umma_idesc_bf16(TILE_M, (uint32_t)HC);
     const uint32_t idesc2 = umma_idesc_bf16(TILE_M, (uint32_t)TR);
     const uint64_t a_desc0 = umma_desc_sw128(smem_u32(a_smem));
@@ -146,10 +176,10 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(const MlpParams p) 
     RingPos rp{0, 0u};
     auto gemm1 = [&](int j) {
       const int buf = j & 1;
-      mbar_wait(&sh->hacc_empty[buf], (((uint32_t)j >> 1) & 1u) ^ 1u);
+      MLP_TIMED(2, mbar_wait(&sh->hacc_empty[buf], (((uint32_t)j >> 1) & 1u) ^ 1u));
       const uint32_t d = tmem_base + (uint32_t)(hbase + buf * HC);
       for (int kb = 0; kb < KB1; ++kb) {
-        mbar_wait(&sh->full[rp.s], rp.ph);
+        MLP_TIMED(1, mbar_wait(&sh->full[rp.s], rp.ph));
         tc_fence_after();
         if (elect_one()) {
           const uint64_t ad = a_desc0 + (uint64_t)(kb * kblk_d16), bd = ring_desc0 + (uint64_t)(rp.s * stage_d16);
@@ -166,12 +196,12 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(const MlpParams p) 
     };
     auto gemm2 = [&](int j) {
       const int buf = j & 1;
-      mbar_wait(&sh->hs_full[buf], ((uint32_t)j >> 1) & 1u);
+      MLP_TIMED(3, mbar_wait(&sh->hs_full[buf], ((uint32_t)j >> 1) & 1u));
       const uint64_t hd0 = hs_desc0 + (uint64_t)(buf * nkk * kblk_d16);
       for (int kk = 0; kk < nkk; ++kk) {
         const int steps = min(4, steps2 - kk * 4);
         for (int tt = 0; tt < nT; ++tt) {
-          mbar_wait(&sh->full[rp.s], rp.ph);
+          MLP_TIMED(4, mbar_wait(&sh->full[rp.s], rp.ph));
           tc_fence_after();
           if (elect_one()) {
             const uint64_t ad = hd0 + (uint64_t)(kk * kblk_d16), bd = ring_desc0 + (uint64_t)(rp.s * stage_d16);
@@ -194,12 +224,12 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(const MlpParams p) 
       if (j + 1 < nj) gemm1(j + 1);
       gemm2(j);
     }
+    MLP_PROF_ADD(5, t_mma0);
   } else {
     // ===== epilogue warps 2..9: thread <-> row; the two warps of a lane group split the columns =====
     const int lg = warp & 3;
     const int half = (warp - 2) >> 2;
     const int r = lg * 32 + lane;
-    const long long m = m0 + r;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
     // 16-column blocks of the hidden chunk owned by this warp
     const int cb_beg = (steps2 & 1) ? (half ? steps2 : 0) : half * (steps2 >> 1);
@@ -208,9 +238,15 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(const MlpParams p) 
     for (int j = 0; j < nj; ++j) {
       const int buf = j & 1;
       const uint32_t ph = ((uint32_t)j >> 1) & 1u;
-      mbar_wait(&sh->hacc_full[buf], ph);
-      mbar_wait(&sh->hs_empty[buf], ph ^ 1u);
+      if (warp == 2) {
+        MLP_TIMED(6, mbar_wait(&sh->hacc_full[buf], ph));
+        MLP_TIMED(7, mbar_wait(&sh->hs_empty[buf], ph ^ 1u));
+      } else {
+        mbar_wait(&sh->hacc_full[buf], ph);
+        mbar_wait(&sh->hs_empty[buf], ph ^ 1u);
+      }
       tc_fence_after();
+      const long long t_g0 = MLP_CLOCK();
       uint8_t* hrow = hs_smem + buf * nkk * A_KBLOCK_BYTES;
       const float* bj = b1s + j * HC;
       const uint32_t t_chunk = lane_addr + (uint32_t)(hbase + buf * HC);
@@ -239,13 +275,27 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(const MlpParams p) 
       fence_proxy_async();
       mbar_arrive(&sh->hacc_empty[buf]);
       mbar_arrive(&sh->hs_full[buf]);
+      if (warp == 2) MLP_PROF_ADD(8, t_g0);
     }
-    mbar_wait(&sh->y_full, 0);
+    // residual rows in the transposed ownership (common.cuh), fetched one column block ahead: the first block is
+    // requested before the wait for the last GEMM2, so its latency hides behind the tail of the MMA pipeline
+    auto load_res = [&](int cb, float4* xr) {
+      const int c = cb * 16 + (lane & 3) * 4;
+#pragma unroll
+      for (int ps = 0; ps < 4; ++ps) {
+        const long long mm = m0 + lg * 32 + ps * 8 + (lane >> 2);
+        xr[ps] = (cb < (C16 >> 4) && c < C && mm < p.M) ? __ldg(reinterpret_cast<const float4*>(p.x + mm * C + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    float4 xr_cur[4], xr_nxt[4];
+    load_res(half, xr_cur);
+    if (warp == 2) MLP_TIMED(9, mbar_wait(&sh->y_full, 0)); else mbar_wait(&sh->y_full, 0);
+    const long long t_f0 = MLP_CLOCK();
     tc_fence_after();
-    // transposed ownership for the residual read and the store (common.cuh); the hidden tiles are free by now and
-    // serve as the per-warp 2 KB scratch
+    // the hidden tiles are free by now and serve as the per-warp 2 KB transposition scratch
     uint8_t* scr = hs_smem + (warp - 2) * EPI_SCRATCH_BYTES;
     for (int cb = half; cb < (C16 >> 4); cb += 2) {
+      load_res(cb + 2, xr_nxt);
       tmem_ld16(lane_addr + (uint32_t)(cb * 16), v);
       tmem_ld_wait();
 #pragma unroll
@@ -258,13 +308,16 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(const MlpParams p) 
           const long long mm = m0 + lg * 32 + ps * 8 + (lane >> 2);
           if (mm >= p.M) continue;
           const float4 y = epi_gather4(scr, ps, lane);
-          const float4 xr = __ldg(reinterpret_cast<const float4*>(p.x + mm * C + c));
-          *reinterpret_cast<float4*>(p.out + mm * C + c) = make_float4(y.x + xr.x, y.y + xr.y, y.z + xr.z, y.w + xr.w);
+          *reinterpret_cast<float4*>(p.out + mm * C + c) = make_float4(y.x + xr_cur[ps].x, y.y + xr_cur[ps].y, y.z + xr_cur[ps].z, y.w + xr_cur[ps].w);
         }
       }
+#pragma unroll
+      for (int ps = 0; ps < 4; ++ps) xr_cur[ps] = xr_nxt[ps];
       __syncwarp();
     }
+    if (warp == 2) MLP_PROF_ADD(10, t_f0);
   }
+  if (warp == 1) MLP_PROF_ADD(11, t_cta0);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
