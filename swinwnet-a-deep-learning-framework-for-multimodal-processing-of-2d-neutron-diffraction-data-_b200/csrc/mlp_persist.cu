@@ -11,6 +11,13 @@
 //                             (staging) -> fp32 out
 // Every global load goes through the TMA engine one tile ahead of its use, so HBM latency is never exposed;
 // the hidden activation never leaves the SM.
+//
+// DIRECT variant (C = 192, rows too wide to stage twice in shared memory): no input producer / staging; the LayerNorm
+// warps read the rows of the NEXT tile straight from global memory (lanes along the row, coalesced) while the MMA /
+// epilogue warps work on the current one, and the final epilogue re-reads the residual (L2) one column block ahead
+// and stores through a per-warp transposition scratch.  Status: parity-green, but with 4 LayerNorm warps and a single
+// A buffer the prologue is not hidden yet — 0.79 ms against 0.73 ms for mlp.cu at M = 483 840 — so it is opt-in
+// (SWN_MLP_PERSIST_MAX_C=192); next step: second A buffer + 8 LayerNorm warps.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -30,7 +37,7 @@ struct MpSmem {
   uint32_t tmem_base;
 };
 
-template <int LPR>
+template <int LPR, bool DIRECT>
 __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -56,6 +63,7 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
   float* lnw = b2s + C16;                                           // [C16]
   float* lnb = lnw + C16;                                           // [C16]
   MpSmem* sh = reinterpret_cast<MpSmem*>(lnb + C16);
+  uint8_t* epi_scratch = reinterpret_cast<uint8_t*>(sh) + ((sizeof(MpSmem) + 15) & ~size_t(15));   // DIRECT: 8 warps x 2 KB
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntiles = (p.M + TILE_M - 1) / TILE_M;
@@ -112,7 +120,7 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
         }
       }
     }
-  } else if (warp == 2) {
+  } else if (warp == 2 && !DIRECT) {
     // ===== input producer: one bulk copy per token row into the padded staging tile =====
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
@@ -203,6 +211,19 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
       const int s = it & 1;
       const long long m0 = (long long)tile * TILE_M;
       const int rows = (int)min((long long)TILE_M, (long long)p.M - m0);
+      if (DIRECT) {
+        // rows straight from global memory, lanes along the row (coalesced), 4 rows in flight per warp
+        mbar_wait(&sh->a_empty, ((uint32_t)it & 1u) ^ 1u);
+        const float* xg = p.x;
+        build_a_tile<32, (LPR == 32 ? 2 : 1), 4, true>(a_smem, C, C16, p.ln_w, p.ln_b, p.ln_eps, warp - 4, MP_LN_WARPS, lane, [&](int r, int k) {
+          const long long mr = m0 + r;
+          if (mr >= p.M) return make_float4(0.f, 0.f, 0.f, 0.f);
+          return __ldg(reinterpret_cast<const float4*>(xg + mr * C + k));
+        });
+        fence_proxy_async();
+        mbar_arrive(&sh->a_full);
+        continue;
+      }
       mbar_wait(&sh->in_full[s], ((uint32_t)it >> 1) & 1u);
       mbar_wait(&sh->a_empty, ((uint32_t)it & 1u) ^ 1u);
       // one thread per row (the staging rows are padded to an odd number of 16-byte chunks, so this is bank
@@ -316,6 +337,41 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
       // final: Y + b2 + residual(staging) -> out
       mbar_wait(&sh->y_full, (uint32_t)it & 1u);
       tc_fence_after();
+      if (DIRECT) {
+        // residual re-read from global (L2) one column block ahead, transposed ownership through the per-warp scratch
+        uint8_t* scr = epi_scratch + (warp - 8) * EPI_SCRATCH_BYTES;
+        auto load_res = [&](int cb, float4* xr) {
+          const int c = cb * 16 + (lane & 3) * 4;
+#pragma unroll
+          for (int ps = 0; ps < 4; ++ps) {
+            const long long mm = (long long)tile * TILE_M + lg * 32 + ps * 8 + (lane >> 2);
+            xr[ps] = (cb < (C16 >> 4) && c < C && mm < p.M) ? __ldg(reinterpret_cast<const float4*>(p.x + mm * C + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        };
+        float4 xr_cur[4], xr_nxt[4];
+        load_res(part, xr_cur);
+        for (int cb = part; cb < (C16 >> 4); cb += MP_EPI_SPLIT) {
+          load_res(cb + MP_EPI_SPLIT, xr_nxt);
+          tmem_ld16(lane_addr + (uint32_t)(cb * 16), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] += b2s[cb * 16 + j];
+          epi_scatter16(scr, v, lane);
+          const int c = cb * 16 + (lane & 3) * 4;
+          if (c < C) {
+#pragma unroll
+            for (int ps = 0; ps < 4; ++ps) {
+              const long long mm = (long long)tile * TILE_M + lg * 32 + ps * 8 + (lane >> 2);
+              if (mm >= p.M) continue;
+              const float4 y = epi_gather4(scr, ps, lane);
+              *reinterpret_cast<float4*>(p.out + mm * C + c) = make_float4(y.x + xr_cur[ps].x, y.y + xr_cur[ps].y, y.z + xr_cur[ps].z, y.w + xr_cur[ps].w);
+            }
+          }
+#pragma unroll
+          for (int ps = 0; ps < 4; ++ps) xr_cur[ps] = xr_nxt[ps];
+          __syncwarp();
+        }
+      } else {
       // out = Y + b2 + residual is formed in place in the staging row (row-per-lane, conflict free), then stored in the
       // transposed ownership (common.cuh): 8 rows x 64 contiguous bytes per warp instruction
       uint8_t* stile = stg + s * TILE_M * rs;
@@ -343,9 +399,10 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
           }
         }
       }
+      }
       tc_fence_before();
       mbar_arrive(&sh->y_empty);
-      mbar_arrive(&sh->in_empty[s]);
+      if (!DIRECT) mbar_arrive(&sh->in_empty[s]);
     }
   }
   tc_fence_before();
@@ -358,7 +415,8 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
 
 int launch_mlp_persist(MlpParams p, int num_sms, cudaStream_t stream) {
   const int C = p.C, C16 = (C + 15) & ~15;
-  SWN_CHECK(p.M > 0 && C >= 4 && C % 4 == 0 && C <= 96, "mlp_persist: unsupported C=%d", C);
+  SWN_CHECK(p.M > 0 && C >= 4 && C % 4 == 0 && C <= 192, "mlp_persist: unsupported C=%d", C);
+  const bool direct = C > 96;    // rows too wide to stage twice: LayerNorm warps read global memory directly
   const int nj = (4 * C) / p.HC;
   const int KB1 = (C16 + 63) >> 6, nkk = (p.HC + 63) >> 6;
   int cols = ((C16 + 31) & ~31) + (nj > 1 ? 2 : 1) * p.HC, tc = 32;
@@ -371,10 +429,10 @@ int launch_mlp_persist(MlpParams p, int num_sms, cudaStream_t stream) {
   }
   p.tmem_cols = tc;
   const int chunks = C / 4;
-  p.row_stride = (chunks + ((chunks & 1) ? 0 : 1)) * 16;
+  p.row_stride = direct ? 0 : (chunks + ((chunks & 1) ? 0 : 1)) * 16;
   const int stage_bytes = (p.HC > p.TR ? p.HC : p.TR) * 128;
   const int fixed = 1024 + (KB1 + 2 * nkk) * A_KBLOCK_BYTES + 2 * TILE_M * p.row_stride + (4 * C + 3 * C16) * 4 +
-                    (int)sizeof(MpSmem) + 64;
+                    (int)sizeof(MpSmem) + 64 + (direct ? 8 * EPI_SCRATCH_BYTES + 16 : 0);
   int stages = (232448 - fixed) / stage_bytes;
   if (stages > 6) stages = 6;
   SWN_CHECK(stages >= 2, "mlp_persist: does not fit in shared memory (C=%d)", C);
@@ -388,10 +446,11 @@ int launch_mlp_persist(MlpParams p, int num_sms, cudaStream_t stream) {
     SWN_CUDA(cudaGetLastError());
     return 0;
   };
-  if (C <= 16) return go(mlp_persist_kernel<4>);
-  if (C <= 32) return go(mlp_persist_kernel<8>);
-  if (C <= 64) return go(mlp_persist_kernel<16>);
-  return go(mlp_persist_kernel<32>);
+  if (direct) return go(mlp_persist_kernel<32, true>);
+  if (C <= 16) return go(mlp_persist_kernel<4, false>);
+  if (C <= 32) return go(mlp_persist_kernel<8, false>);
+  if (C <= 64) return go(mlp_persist_kernel<16, false>);
+  return go(mlp_persist_kernel<32, false>);
 }
 
 }  // namespace swn
