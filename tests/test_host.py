@@ -156,3 +156,47 @@ def test_checkpoint_ingestion_variants():
     import pytest
     with pytest.raises(ValueError):
         ck.load_state_dict_any([1, 2, 3])
+
+
+def test_fused_block_packing_folds_are_exact_algebra():
+    """packing.pack_fused_block (host side of csrc/swin_fused.cu): un-swizzling the packed tiles and replaying the kernel's
+    arithmetic in fp32 torch — (x - mean) * rstd against the folded weights, exp2 softmax against the bias-fragment
+    images, row sums from the ones block — reproduces the oracle block's qkv, attention logits and fc1 pre-activations."""
+    import math
+    import torch
+    from swinwnet_b200 import packing
+    from oracle import swinwnet_oracle as O
+    torch.manual_seed(0)
+    C, nH = 24, 3
+    hd = C // nH
+    shp = [(C,), (C,), (3 * C, C), (3 * C,), (81, nH), (C, C), (C,), (C,), (C,), (4 * C, C), (4 * C,), (C, 4 * C), (C,)]
+    n1w, n1b, Wqkv, bqkv, table, Wproj, bproj, n2w, n2b, W1, b1, W2, b2 = [torch.randn(*s) * 0.3 + (1.0 if i in (0, 7) else 0.0)
+                                                                           for i, s in enumerate(shp)]
+    Wpk, fpk = packing.pack_fused_block(n1w, n1b, Wqkv, bqkv, table, Wproj, bproj, n2w, n2b, W1, b1, W2, b2, nH)
+    K16, NQ, HC, nj, ones = packing.fused_block_geometry(C)
+    tiles = packing.unswizzle_tiles(Wpk[:NQ * 64].view(NQ, 64)).float()                 # Wqkv' image [NQ, 64]
+    bq_fold, bq_plain = fpk[:NQ], fpk[NQ:2 * NQ]
+    x = torch.randn(7, C) * 2 + 0.5
+    xn = (x - x.mean(-1, keepdim=True)) * torch.rsqrt(x.var(-1, unbiased=False, keepdim=True) + 1e-5)
+    qkv_k = xn @ tiles[:, :C].t() + bq_fold                                              # what the kernel's GEMM + bias gives
+    ref = O.linear(O.layer_norm(x, n1w, n1b), Wqkv, bqkv)
+    qs = hd ** -0.5 * math.log2(math.e)
+    ref = torch.cat([ref[:, :C] * qs, ref[:, C:]], 1)
+    tol = 2e-3 * ref.abs().max()                                                         # 16-bit rounding of the packed weights
+    assert (qkv_k[:, :3 * C] - ref).abs().max() <= tol
+    assert torch.equal(qkv_k[:, ones:ones + 8], torch.ones(7, 8))                        # ones block: zero weights, bias 1
+    assert torch.allclose(bq_plain[:3 * C], torch.cat([bqkv[:C] * qs, bqkv[C:]]), atol=1e-6)   # q/k/v of zero-padded tokens
+    # bias fragment images: element (mt, nt, lane, e) <-> (row, key) of the 32x32 tile
+    frag = fpk[2 * NQ + 2 * K16 + 4 * C:].view(nH, 2, 4, 32, 4)
+    idx = O.rel_pos_index()
+    for (h, mt, nt, lane, e) in ((0, 0, 0, 0, 0), (1, 1, 2, 13, 3), (2, 0, 3, 31, 1), (2, 1, 1, 5, 2)):
+        row, key = mt * 16 + lane // 4 + (e // 2) * 8, nt * 8 + (lane % 4) * 2 + e % 2
+        want = -1e30 if key >= 25 else (0.0 if row >= 25 else table[idx[row, key], h].item() * math.log2(math.e))
+        assert abs(frag[h, mt, nt, lane, e].item() - want) <= 1e-6 * max(1.0, abs(want))
+    # fc1 with the norm2 affine folded in
+    off = (NQ + K16) * 64
+    W1img = packing.unswizzle_tiles(Wpk[off:off + nj * HC * 64].view(nj * HC, 64)).float()[:, :C]
+    b1_fold = fpk[2 * NQ + K16:2 * NQ + K16 + 4 * C]
+    h_k = xn @ W1img.t() + b1_fold
+    h_ref = O.linear(O.layer_norm(x, n2w, n2b), W1, b1)
+    assert (h_k - h_ref).abs().max() <= 2e-3 * h_ref.abs().max()
