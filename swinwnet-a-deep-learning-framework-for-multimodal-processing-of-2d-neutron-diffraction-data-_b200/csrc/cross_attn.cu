@@ -9,8 +9,11 @@
 
 namespace swn {
 
-constexpr int CA_THREADS = 128;  // 4 warps x 16 query rows
-constexpr int CA_BQ = 64, CA_BK = 64;
+// 8 warps x 16 query rows per CTA: every CTA streams the whole K/V of its (batch, head) from L2, so the query tile
+// height sets the L2 traffic (BQ = 64 moved 2.8 GB per call at L = 1920 and was bound by it); K/V tiles are
+// double-buffered with cp.async so the next tile lands while the current one is in the tensor cores.
+constexpr int CA_THREADS = 256;
+constexpr int CA_BQ = 128, CA_BK = 64;
 
 __device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -27,15 +30,13 @@ __global__ void __launch_bounds__(CA_THREADS) cross_attn_kernel(const CrossAttnP
   constexpr int LDS = HD + 8;  // padded smem row (bf16 elements)
   extern __shared__ __align__(16) uint8_t smem_raw[];
   op_t* q_s = reinterpret_cast<op_t*>(smem_raw);
-  op_t* k_s = q_s + CA_BQ * LDS;
-  op_t* v_s = k_s + CA_BK * LDS;
+  op_t* kv_s = q_s + CA_BQ * LDS;   // [2 stages][K tile | V tile][CA_BK][LDS]
 
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * CA_BQ;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
   const int C = p.C;
   const op_t* qg = p.q + ((long long)b * p.Lq) * C + h * HD;
   const op_t* kg = p.kv + ((long long)b * p.Lk) * (2 * C) + h * HD;
-  const op_t* vg = kg + C;
 
   constexpr int VPR = HD / 8;  // 16-byte vectors per row
   for (int i = threadIdx.x; i < CA_BQ * VPR; i += CA_THREADS) {
@@ -63,19 +64,31 @@ __global__ void __launch_bounds__(CA_THREADS) cross_attn_kernel(const CrossAttnP
   float m_run[2] = {-1e30f, -1e30f}, l_run[2] = {0.f, 0.f};
   const float sl2 = rsqrtf((float)HD) * 1.4426950408889634f;
 
-  for (int k0 = 0; k0 < p.Lk; k0 += CA_BK) {
-    __syncthreads();  // previous tile fully consumed
+  auto issue_kv = [&](int k0, int stage) {
+    op_t* k_dst = kv_s + stage * 2 * CA_BK * LDS;
+    op_t* v_dst = k_dst + CA_BK * LDS;
     for (int i = threadIdx.x; i < CA_BK * VPR; i += CA_THREADS) {
       const int r = i / VPR, c = (i % VPR) * 8;
-      uint4 kv = make_uint4(0u, 0u, 0u, 0u), vv = kv;
-      if (k0 + r < p.Lk) {
-        kv = *reinterpret_cast<const uint4*>(kg + (long long)(k0 + r) * (2 * C) + c);
-        vv = *reinterpret_cast<const uint4*>(vg + (long long)(k0 + r) * (2 * C) + c);
-      }
-      *reinterpret_cast<uint4*>(k_s + r * LDS + c) = kv;
-      *reinterpret_cast<uint4*>(v_s + r * LDS + c) = vv;
+      const bool ok = k0 + r < p.Lk;
+      const op_t* ksrc = kg + (long long)(ok ? k0 + r : 0) * (2 * C) + c;
+      const uint32_t n = ok ? 16u : 0u;     // zero-fill the key tail
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(k_dst + r * LDS + c)), "l"(ksrc), "r"(n) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(v_dst + r * LDS + c)), "l"(ksrc + C), "r"(n) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  issue_kv(0, 0);
+  int stage = 0;
+  for (int k0 = 0; k0 < p.Lk; k0 += CA_BK, stage ^= 1) {
+    if (k0 + CA_BK < p.Lk) {
+      issue_kv(k0 + CA_BK, stage ^ 1);     // the other stage was released by the barrier at the end of the last iteration
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
+    const op_t* k_s = kv_s + stage * 2 * CA_BK * LDS;
+    const op_t* v_s = k_s + CA_BK * LDS;
 
     float s[CA_BK / 8][4];
 #pragma unroll
@@ -107,7 +120,7 @@ __global__ void __launch_bounds__(CA_THREADS) cross_attn_kernel(const CrossAttnP
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
       const float m_new = fmaxf(m_run[r], mx[r]);
-      corr[r] = exp2f(m_run[r] - m_new);
+      corr[r] = ex2_approx(m_run[r] - m_new);
       m_run[r] = m_new;
       l_run[r] *= corr[r];
     }
@@ -116,7 +129,7 @@ __global__ void __launch_bounds__(CA_THREADS) cross_attn_kernel(const CrossAttnP
     for (int n = 0; n < CA_BK / 8; ++n) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float pv = exp2f(s[n][e] - m_run[e >> 1]);
+        const float pv = ex2_approx(s[n][e] - m_run[e >> 1]);
         s[n][e] = pv;
         rs[e >> 1] += pv;
       }
@@ -146,6 +159,7 @@ __global__ void __launch_bounds__(CA_THREADS) cross_attn_kernel(const CrossAttnP
         mma_bf16_16816(o[n], pa, b0, b1);
       }
     }
+    __syncthreads();   // this stage may be overwritten by the prefetch issued in the next iteration
   }
   // finalize: quad-reduce the row sums, normalise, store bf16
 #pragma unroll
@@ -169,7 +183,7 @@ int launch_cross_attn(CrossAttnParams p, cudaStream_t stream) {
   SWN_CHECK(hd == 64 || hd == 128, "cross_attn: unsupported head_dim %d (embed_dim must be 48)", hd);
   SWN_CHECK(p.Lq > 0 && p.Lk > 0 && p.B > 0 && p.B <= 65535, "cross_attn: bad sizes");
   dim3 grid((p.Lq + CA_BQ - 1) / CA_BQ, p.nH, p.B);
-  const size_t smem = (size_t)(CA_BQ + 2 * CA_BK) * (hd + 8) * 2;
+  const size_t smem = (size_t)(CA_BQ + 4 * CA_BK) * (hd + 8) * 2;
   auto go = [&](auto kern) -> int {
     SWN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, CA_THREADS, smem, stream>>>(p);
