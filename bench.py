@@ -133,6 +133,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="diffractions per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="also time CUDA-graph replay of the pipeline (matters at small --batch, where a pass is launch-bound); reported under \"graph\"")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -156,6 +157,7 @@ def main():
     model = S.SwinWNet(error_matrix=True, depths=DEPTHS)
     model.load_state_dict(benchdata.make_state_dict(man["wnet_em"], seed=1), strict=True)
     inf = S.SwinWNetInference(model, dev, max_batch=64)
+    inf_fast = S.SwinWNetInference(model, dev, max_batch=64, cuda_graph=True) if args.graph else inf
     B = args.batch
     base = benchdata.synthetic_diffractions(min(B, 8), seed=100 + rank, two_channel=False)
     x_host = base.repeat((B + base.shape[0] - 1) // base.shape[0], 1, 1, 1)[:B].contiguous()
@@ -247,6 +249,12 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=3)
 
+    graph_info = None
+    if args.graph:
+        for _ in range(3):
+            inf_fast(x_dev)
+        ms_g = timed(lambda: inf_fast(x_dev), args.steps)
+        graph_info = {"value": whole_job_rate(B, world, args.steps, ms_g), "unit": UNIT, "ms_per_step": ms_g / args.steps}
     value = whole_job_rate(B, world, args.steps, ms)
     e2e_v = whole_job_rate(B, world, args.steps, ms_e2e)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W_,
@@ -267,6 +275,8 @@ def main():
                          "hbm_achieved_gbs": kern[dom]["achieved_gbs"], "hbm_peak_gbs": pk["hbm"], "hbm_frac": kern[dom]["hbm_frac"]},
             "kernels": kern,
             "clocks": sampler.summary()}
+    if graph_info:
+        line["graph"] = graph_info
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count()
         torch.set_num_threads(cores)

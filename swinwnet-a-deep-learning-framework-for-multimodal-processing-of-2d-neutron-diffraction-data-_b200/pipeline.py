@@ -9,11 +9,17 @@ from . import ops
 
 
 class SwinWNetInference:
-    def __init__(self, model, device, max_batch=64):
+    def __init__(self, model, device, max_batch=64, cuda_graph=False):
+        """``cuda_graph=True``: the ~220 kernel launches of a pipeline pass are captured once per input shape (and per
+        state of the model parameters) into a CUDA graph and replayed — 7.1 -> ~2 ms per call at batch 1, where the pass is
+        launch-bound.  The returned / cached tensors are then the graph's static output buffers: they are overwritten by
+        the next call with the same input shape (clone them to keep them)."""
         self.model = model.to(device)
         self.device = device
         self.model.eval()
         self.max_batch = max_batch
+        self.cuda_graph = cuda_graph
+        self._graphs = {}
         self._copy_streams = None
         self.host_done = None          # CUDA event: the last run_host() result has landed in host memory
         self._reset_outputs()
@@ -48,6 +54,36 @@ class SwinWNetInference:
                     upscaled_norm=upscaled_norm, upscaled_denorm=upscaled_denorm, seg_map_hr=seg_map_hr,
                     images_masked_hr=masked_hr, seg_lr_logits=seg, seg_hr_logits=seg_high)
 
+    def _weights_key(self):
+        # (storage, in-place version) of every parameter: a graph bakes the packed-weight pointers in, so it is only
+        # replayed while the parameters it was captured with are untouched
+        return tuple((p.data_ptr(), p._version) for p in self.model.parameters())
+
+    def _run_graphed(self, images, two_channel):
+        images = images.to(self.device).float().contiguous()
+        key = (tuple(images.shape), bool(two_channel))
+        wkey = self._weights_key()
+        entry = self._graphs.get(key)
+        if entry is None or entry[0] != wkey:
+            static_in = images.clone()
+            cur = torch.cuda.current_stream(images.device)
+            side = torch.cuda.Stream(images.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):           # warm-up outside the capture: weight packing, function attributes
+                for _ in range(2):
+                    self._run(static_in, two_channel)
+            cur.wait_stream(side)
+            torch.cuda.synchronize(images.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self._run(static_in, two_channel)
+            entry = (wkey, graph, static_in, out)
+            self._graphs[key] = entry
+        _, graph, static_in, out = entry
+        static_in.copy_(images)
+        graph.replay()
+        return out
+
     def __call__(self, images, two_channel=True):
         """two_channel=False is the manual 1-channel call pattern (the reference class itself cannot drive a
         diffraction-only model)."""
@@ -55,7 +91,7 @@ class SwinWNetInference:
         with torch.no_grad():
             B = images.shape[0]
             if B <= self.max_batch:
-                out = self._run(images, two_channel)
+                out = self._run_graphed(images, two_channel) if self.cuda_graph else self._run(images, two_channel)
             else:
                 parts = [self._run(images[i:i + self.max_batch], two_channel) for i in range(0, B, self.max_batch)]
                 out = {k: torch.cat([p[k] for p in parts], 0) for k in parts[0]}

@@ -132,6 +132,24 @@ def test_batch_independence_and_determinism_full_size(wnet_em):
     assert full.shape == (3, 2, 500, 960) and torch.isfinite(full).all()
 
 
+def test_cuda_graph_replay_matches_eager_and_tracks_weights(manifest):
+    """cuda_graph=True: replayed pipeline == eager pipeline bit for bit, for repeated calls, a second input shape, and
+    after the parameters were replaced (the graph must be re-captured, not replayed with stale packed weights)."""
+    m = S.SwinWNet(error_matrix=True, depths=D2)
+    m.load_state_dict(O.make_state_dict(manifest["wnet_em"], seed=1), strict=True)
+    eager = S.SwinWNetInference(m, DEV)
+    graphed = S.SwinWNetInference(m, DEV, cuda_graph=True)
+    xa = O.synthetic_diffractions(2, seed=51, H=60, W=80, two_channel=False).to(DEV)
+    xb = O.synthetic_diffractions(1, seed=52, H=40, W=100, two_channel=False).to(DEV)
+    for x in (xa, xb, xa * 1.5, xa):
+        ref = eager(x).clone()
+        assert torch.equal(graphed(x), ref)
+        assert torch.equal(graphed.seg_map_lr, eager.seg_map_lr)
+    m.load_state_dict(O.make_state_dict(manifest["wnet_em"], seed=2), strict=True)
+    ref = eager(xa).clone()
+    assert torch.equal(graphed(xa), ref)
+
+
 def test_run_host_pipelined_copies_match_device_call(wnet_em):
     """public host-data call (pinned host in -> pinned host out, chunked, copies overlapped with compute on side streams)
     returns exactly what the device call returns, chunk boundaries and ragged last chunk included."""
