@@ -122,6 +122,32 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return fmaf(hx, t, hx);
 }
 
+// GELU of two pre-activations, packed as two 16-bit MMA operands.  fp16 build: the whole evaluation runs on packed
+// half2 arithmetic (1 cvt + 6 HFMA2-class + the two halves of tanh.approx.f16x2 for TWO elements, against 2 x 8 + pack
+// in fp32); the result is rounded to fp16 anyway, and a float64 replay of this exact op sequence (tests/test_host.py)
+// stays within 1.7x the rms error of "fp32 GELU, then one rounding" — a few 1e-4 on O(1) activations.  The bf16 build
+// (8 mantissa bits) keeps the fp32 evaluation.  Opt out with -DSWN_GELU_FP32=1.
+#ifndef SWN_GELU_FP32
+#define SWN_GELU_FP32 0
+#endif
+__device__ __forceinline__ uint32_t gelu_pack2(float a, float b) {
+#if SWN_OPERAND_BF16 || SWN_GELU_FP32
+  return pack_op(gelu_fast(a), gelu_fast(b));
+#else
+  const __half2 x = __floats2half2_rn(a, b);
+  const __half2 x2 = __hmin2(__hmul2(x, x), __float2half2_rn(49.0f));
+  __half2 pz = __hfma2(__float2half2_rn(-3.58732362e-4f), x2, __float2half2_rn(3.70503451e-2f));
+  pz = __hfma2(pz, x2, __float2half2_rn(7.97458471e-1f));
+  const __half2 u = __hmul2(x, pz);
+  uint32_t ur = *reinterpret_cast<const uint32_t*>(&u), tr;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(tr) : "r"(ur));
+  const __half2 t = *reinterpret_cast<const __half2*>(&tr);
+  const __half2 hx = __hmul2(x, __float2half2_rn(0.5f));
+  const __half2 g = __hfma2(hx, t, hx);
+  return *reinterpret_cast<const uint32_t*>(&g);
+#endif
+}
+
 // ---------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------

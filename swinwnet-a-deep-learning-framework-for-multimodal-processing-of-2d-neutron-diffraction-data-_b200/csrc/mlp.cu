@@ -263,8 +263,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(const MlpParams p) 
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float4 bb = *reinterpret_cast<const float4*>(bj + k + 4 * i);
-            pk[2 * i] = pack_op(gelu_fast(v[hb * 16 + 4 * i] + bb.x), gelu_fast(v[hb * 16 + 4 * i + 1] + bb.y));
-            pk[2 * i + 1] = pack_op(gelu_fast(v[hb * 16 + 4 * i + 2] + bb.z), gelu_fast(v[hb * 16 + 4 * i + 3] + bb.w));
+            pk[2 * i] = gelu_pack2(v[hb * 16 + 4 * i] + bb.x, v[hb * 16 + 4 * i + 1] + bb.y);
+            pk[2 * i + 1] = gelu_pack2(v[hb * 16 + 4 * i + 2] + bb.z, v[hb * 16 + 4 * i + 3] + bb.w);
           }
           uint8_t* kb_base = hrow + (k >> 6) * A_KBLOCK_BYTES;
           *reinterpret_cast<uint4*>(kb_base + sw128_offset(r, k & 63)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);

@@ -321,8 +321,8 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const float4 bb = *reinterpret_cast<const float4*>(bj + k + 4 * q);
-              pk[2 * q] = pack_op(gelu_fast(vv[i][4 * q] + bb.x), gelu_fast(vv[i][4 * q + 1] + bb.y));
-              pk[2 * q + 1] = pack_op(gelu_fast(vv[i][4 * q + 2] + bb.z), gelu_fast(vv[i][4 * q + 3] + bb.w));
+              pk[2 * q] = gelu_pack2(vv[i][4 * q] + bb.x, vv[i][4 * q + 1] + bb.y);
+              pk[2 * q + 1] = gelu_pack2(vv[i][4 * q + 2] + bb.z, vv[i][4 * q + 3] + bb.w);
             }
             uint8_t* kb_base = hrow + (k >> 6) * A_KBLOCK_BYTES;
             *reinterpret_cast<uint4*>(kb_base + sw128_offset(r, k & 63)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);

@@ -562,7 +562,7 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
               const float* vv = v[j * UPT + ui];
               uint32_t pk[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) pk[i] = pack_op(gelu_fast(vv[2 * i] + bj[2 * i]), gelu_fast(vv[2 * i + 1] + bj[2 * i + 1]));
+              for (int i = 0; i < 8; ++i) pk[i] = gelu_pack2(vv[2 * i] + bj[2 * i], vv[2 * i + 1] + bj[2 * i + 1]);
               uint8_t* hs = u_s + j * A_KBLOCK_BYTES;
               *reinterpret_cast<uint4*>(hs + sw128_offset(row, cu * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
               *reinterpret_cast<uint4*>(hs + sw128_offset(row, cu * 16 + 8)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
@@ -608,7 +608,7 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
             uint32_t pk[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-              pk[i] = pack_op(gelu_fast(v[2 * i] + bj[cu * 16 + 2 * i]), gelu_fast(v[2 * i + 1] + bj[cu * 16 + 2 * i + 1]));
+              pk[i] = gelu_pack2(v[2 * i] + bj[cu * 16 + 2 * i], v[2 * i + 1] + bj[cu * 16 + 2 * i + 1]);
             *reinterpret_cast<uint4*>(hs + sw128_offset(row, cu * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             *reinterpret_cast<uint4*>(hs + sw128_offset(row, cu * 16 + 8)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           }
