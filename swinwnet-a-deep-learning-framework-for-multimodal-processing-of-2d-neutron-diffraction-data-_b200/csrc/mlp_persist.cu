@@ -23,6 +23,25 @@
 
 namespace swn {
 
+// profiling aid (SWN_NVCC_EXTRA=-DSWN_MLP_PROFILE=1, tools/mlp_phase_profile.py); compiled out of the product build
+#ifndef SWN_MLP_PROFILE
+#define SWN_MLP_PROFILE 0
+#endif
+#if SWN_MLP_PROFILE
+#define MP_TIMED(slot, stmt)                                                                          \
+  do {                                                                                                \
+    if (p.phase_cycles) {                                                                             \
+      const long long _t0 = clock64();                                                                \
+      stmt;                                                                                           \
+      if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.phase_cycles + (slot)), (unsigned long long)(clock64() - _t0)); \
+    } else {                                                                                          \
+      stmt;                                                                                           \
+    }                                                                                                 \
+  } while (0)
+#else
+#define MP_TIMED(slot, stmt) do { stmt; } while (0)
+#endif
+
 constexpr int MP_EPI_SPLIT = 2;                 // epilogue warps per TMEM lane group (they split the columns)
 constexpr int MP_WARPS = 8 + 4 * MP_EPI_SPLIT;
 constexpr int MP_THREADS = MP_WARPS * 32;
@@ -150,10 +169,10 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
       const int g0 = it * nj;  // global chunk counter of this tile's first chunk
       auto gemm1 = [&](int j) {
         const int g = g0 + j, buf = g & 1;
-        mbar_wait(&sh->hacc_empty[buf], (((uint32_t)g >> 1) & 1u) ^ 1u);
+        MP_TIMED(2, mbar_wait(&sh->hacc_empty[buf], (((uint32_t)g >> 1) & 1u) ^ 1u));
         const uint32_t d = tmem_base + (uint32_t)(hbase + buf * HC);
         for (int kb = 0; kb < KB1; ++kb) {
-          mbar_wait(&sh->full[rp.s], rp.ph);
+          MP_TIMED(1, mbar_wait(&sh->full[rp.s], rp.ph));
           tc_fence_after();
           if (elect_one()) {
             const uint64_t ad = a_desc0 + (uint64_t)(kb * kblk_d16), bd = ring_desc0 + (uint64_t)(rp.s * stage_d16);
@@ -173,13 +192,13 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
       };
       auto gemm2 = [&](int j) {
         const int g = g0 + j, buf = g & 1;
-        mbar_wait(&sh->hs_full[buf], ((uint32_t)g >> 1) & 1u);
-        if (j == 0) mbar_wait(&sh->y_empty, ((uint32_t)it & 1u) ^ 1u);  // previous tile's Y drained
+        MP_TIMED(3, mbar_wait(&sh->hs_full[buf], ((uint32_t)g >> 1) & 1u));
+        if (j == 0) MP_TIMED(5, mbar_wait(&sh->y_empty, ((uint32_t)it & 1u) ^ 1u));  // previous tile's Y drained
         const uint64_t hd0 = hs_desc0 + (uint64_t)(buf * nkk * kblk_d16);
         for (int kk = 0; kk < nkk; ++kk) {
           const int steps = min(4, steps2 - kk * 4);
           for (int tt = 0; tt < nT; ++tt) {
-            mbar_wait(&sh->full[rp.s], rp.ph);
+            MP_TIMED(4, mbar_wait(&sh->full[rp.s], rp.ph));
             tc_fence_after();
             if (elect_one()) {
               const uint64_t ad = hd0 + (uint64_t)(kk * kblk_d16), bd = ring_desc0 + (uint64_t)(rp.s * stage_d16);
@@ -197,7 +216,7 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
           }
         }
       };
-      mbar_wait(&sh->a_full, (uint32_t)it & 1u);
+      MP_TIMED(0, mbar_wait(&sh->a_full, (uint32_t)it & 1u));
       gemm1(0);
       for (int j = 0; j < nj; ++j) {
         if (j + 1 < nj) gemm1(j + 1);
@@ -224,8 +243,9 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
         mbar_arrive(&sh->a_full);
         continue;
       }
-      mbar_wait(&sh->in_full[s], ((uint32_t)it >> 1) & 1u);
-      mbar_wait(&sh->a_empty, ((uint32_t)it & 1u) ^ 1u);
+      if (warp == 4) { MP_TIMED(12, mbar_wait(&sh->in_full[s], ((uint32_t)it >> 1) & 1u)); MP_TIMED(13, mbar_wait(&sh->a_empty, ((uint32_t)it & 1u) ^ 1u)); }
+      else { mbar_wait(&sh->in_full[s], ((uint32_t)it >> 1) & 1u); mbar_wait(&sh->a_empty, ((uint32_t)it & 1u) ^ 1u); }
+      const long long t_ln0 = SWN_MLP_PROFILE ? clock64() : 0;
       // one thread per row (the staging rows are padded to an odd number of 16-byte chunks, so this is bank
       // conflict free): no shuffles, long independent instruction streams.  Shifted one-pass moments.
       const int row = (warp - 4) * 32 + lane;
@@ -273,6 +293,9 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
       }
       fence_proxy_async();
       mbar_arrive(&sh->a_full);
+#if SWN_MLP_PROFILE
+      if (p.phase_cycles && warp == 4 && lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.phase_cycles + 14), (unsigned long long)(clock64() - t_ln0));
+#endif
     }
   } else if (warp >= 8) {
     // ===== epilogue warps 8..: MP_EPI_SPLIT warps per TMEM lane group split the 16-column blocks =====
@@ -300,9 +323,10 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
       for (int j = 0; j < nj; ++j) {
         const int g = it * nj + j, buf = g & 1;
         const uint32_t ph = ((uint32_t)g >> 1) & 1u;
-        mbar_wait(&sh->hacc_full[buf], ph);
-        mbar_wait(&sh->hs_empty[buf], ph ^ 1u);
+        if (warp == 8) { MP_TIMED(6, mbar_wait(&sh->hacc_full[buf], ph)); MP_TIMED(7, mbar_wait(&sh->hs_empty[buf], ph ^ 1u)); }
+        else { mbar_wait(&sh->hacc_full[buf], ph); mbar_wait(&sh->hs_empty[buf], ph ^ 1u); }
         tc_fence_after();
+        const long long t_g0 = SWN_MLP_PROFILE ? clock64() : 0;
         uint8_t* hrow = hs_smem + buf * nkk * A_KBLOCK_BYTES;
         const float* bj = b1s + j * HC;
         const uint32_t t_chunk = lane_addr + (uint32_t)(hbase + buf * HC);
@@ -333,10 +357,14 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
         fence_proxy_async();
         mbar_arrive(&sh->hacc_empty[buf]);
         mbar_arrive(&sh->hs_full[buf]);
+#if SWN_MLP_PROFILE
+        if (p.phase_cycles && warp == 8 && lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.phase_cycles + 8), (unsigned long long)(clock64() - t_g0));
+#endif
       }
       // final: Y + b2 + residual(staging) -> out
-      mbar_wait(&sh->y_full, (uint32_t)it & 1u);
+      if (warp == 8) MP_TIMED(9, mbar_wait(&sh->y_full, (uint32_t)it & 1u)); else mbar_wait(&sh->y_full, (uint32_t)it & 1u);
       tc_fence_after();
+      const long long t_f0 = SWN_MLP_PROFILE ? clock64() : 0;
       if (DIRECT) {
         // residual re-read from global (L2) one column block ahead, transposed ownership through the per-warp scratch
         uint8_t* scr = epi_scratch + (warp - 8) * EPI_SCRATCH_BYTES;
@@ -400,6 +428,9 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
         }
       }
       }
+#if SWN_MLP_PROFILE
+      if (p.phase_cycles && warp == 8 && lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.phase_cycles + 10), (unsigned long long)(clock64() - t_f0));
+#endif
       tc_fence_before();
       mbar_arrive(&sh->y_empty);
       if (!DIRECT) mbar_arrive(&sh->in_empty[s]);

@@ -49,3 +49,48 @@ def test_shard_bounds_cover_everything():
             spans = [bench.shard_bounds(n, r, world) for r in range(world)]
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+
+
+def _grad_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import swinwnet_b200 as S
+    torch.manual_seed(0)                                   # replicated parameters
+    model = torch.nn.ModuleDict({"enc": torch.nn.Linear(6, 5), "dec": torch.nn.Linear(5, 3), "unused": torch.nn.Linear(4, 4),
+                                 "frozen": torch.nn.Linear(2, 2)})
+    for p in model["frozen"].parameters():
+        p.requires_grad_(False)
+    red = S.dist.GradReducer(model)
+    g = torch.Generator().manual_seed(100 + rank)          # different data shard per rank
+    x = torch.randn(7, 6, generator=g)
+    h = model["enc"](x)
+    loss = (model["dec"](h) ** 2).mean() if rank == 0 else (h ** 2).mean()   # rank 1 never touches "dec": grad None there
+    loss.backward()
+    local = {n: (None if p.grad is None else p.grad.clone()) for n, p in model.named_parameters()}
+    n_red = red.reduce()
+    out.put((rank, n_red, local, {n: (None if p.grad is None else p.grad.clone()) for n, p in model.named_parameters()}))
+    dist.destroy_process_group()
+
+
+def test_grad_reducer_buckets_average_and_tolerate_missing_grads():
+    """config 5 plumbing: per-sub-module buckets, sum / world size, gradients missing on one rank count as zeros,
+    gradients missing everywhere stay None, frozen parameters are left alone."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, 29641, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=180) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, n0, loc0, red0), (_, n1, loc1, red1) = res
+    assert n0 == n1 == 6 * 5 + 5 + 5 * 3 + 3
+    for name in red0:
+        if name.startswith(("unused", "frozen")):
+            assert red0[name] is None and red1[name] is None
+            continue
+        a = loc0[name] if loc0[name] is not None else torch.zeros_like(red0[name])
+        b = loc1[name] if loc1[name] is not None else torch.zeros_like(red0[name])
+        assert torch.allclose(red0[name], (a + b) / 2, atol=1e-7) and torch.equal(red0[name], red1[name])
+    assert loc1["dec.weight"] is None and red1["dec.weight"] is not None

@@ -34,7 +34,9 @@ t = buf.cpu().tolist()
 ntiles = (M + 127) // 128
 names = ["MMA: wait A tile", "MMA: wait W1 tiles", "MMA: wait Hacc free", "MMA: wait hidden tile", "MMA: wait W2 tiles", "MMA warp total",
          "EPI: wait Hacc full", "EPI: wait hidden free", "EPI: GELU chunks", "EPI: wait Y", "EPI: final epilogue", "CTA total",
-         "prologue (LN -> A)"]
+         "prologue (LN -> A) | persist: LN wait rows", "persist: LN wait A free", "persist: LN compute", ""]
+if C <= 96:
+    names[5] = "MMA: wait Y drained"
 print(f"C={C} M={M} HC={HC} TR={TR} tiles={ntiles}")
 for i, n in enumerate(names):
     print(f"{n:24s} {t[i] / ntiles:10.0f} cycles / tile")
