@@ -429,7 +429,11 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
         const float* bb = (tokr >= 0 ? bqkv : bqkv_pad) + cu * 16;
         uint32_t pk[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) pk[i] = pack_op(v[2 * i] + bb[2 * i], v[2 * i + 1] + bb[2 * i + 1]);
+        for (int i = 0; i < 4; ++i) {   // bias as float4: scalar broadcast loads cost a shared-memory wavefront each
+          const float4 b4 = *reinterpret_cast<const float4*>(bb + 4 * i);
+          pk[2 * i] = pack_op(v[4 * i] + b4.x, v[4 * i + 1] + b4.y);
+          pk[2 * i + 1] = pack_op(v[4 * i + 2] + b4.z, v[4 * i + 3] + b4.w);
+        }
         *reinterpret_cast<uint4*>(qrow + cu * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         *reinterpret_cast<uint4*>(qrow + cu * 16 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
       }
@@ -562,7 +566,11 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
               const float* vv = v[j * UPT + ui];
               uint32_t pk[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) pk[i] = gelu_pack2(vv[2 * i] + bj[2 * i], vv[2 * i + 1] + bj[2 * i + 1]);
+              for (int i = 0; i < 4; ++i) {
+                const float4 b4 = *reinterpret_cast<const float4*>(bj + 4 * i);
+                pk[2 * i] = gelu_pack2(vv[4 * i] + b4.x, vv[4 * i + 1] + b4.y);
+                pk[2 * i + 1] = gelu_pack2(vv[4 * i + 2] + b4.z, vv[4 * i + 3] + b4.w);
+              }
               uint8_t* hs = u_s + j * A_KBLOCK_BYTES;
               *reinterpret_cast<uint4*>(hs + sw128_offset(row, cu * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
               *reinterpret_cast<uint4*>(hs + sw128_offset(row, cu * 16 + 8)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
@@ -607,8 +615,11 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
             tmem_ld_wait();
             uint32_t pk[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              pk[i] = gelu_pack2(v[2 * i] + bj[cu * 16 + 2 * i], v[2 * i + 1] + bj[cu * 16 + 2 * i + 1]);
+            for (int i = 0; i < 4; ++i) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bj + cu * 16 + 4 * i);
+              pk[2 * i] = gelu_pack2(v[4 * i] + b4.x, v[4 * i + 1] + b4.y);
+              pk[2 * i + 1] = gelu_pack2(v[4 * i + 2] + b4.z, v[4 * i + 3] + b4.w);
+            }
             *reinterpret_cast<uint4*>(hs + sw128_offset(row, cu * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             *reinterpret_cast<uint4*>(hs + sw128_offset(row, cu * 16 + 8)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           }
