@@ -56,6 +56,7 @@ struct MlpParams {
   int HC;                   // hidden chunk width
   int TR;                   // fc2 output rows per weight tile
   int stages, tmem_cols;    // filled in by the launcher
+  int n_hacc;               // mlp.cu: hidden accumulators in TMEM (2 = double buffered)
   int row_stride;           // mlp_persist: staging row stride in bytes (filled in by the launcher)
   long long* phase_cycles;  // optional [16] clock64 sums (profiling aid, see swn_set_phase_profile)
 };

@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(const MlpParams p) 
   const int nkk = (HC + 63) >> 6, steps2 = HC >> 4;
   const int nT = C16 / TR;
   const int hbase = (C16 + 31) & ~31;  // TMEM column of the first hidden accumulator
+  const bool hacc1 = p.n_hacc == 1;    // single hidden accumulator (TMEM too small for two at this HC): GEMM1(j+1) waits for epilogue(j)
   const int stage_bytes = max(HC, TR) * 128;
   const int w1_bytes = HC * 128, w2_bytes = TR * 128;
 
@@ -175,8 +176,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(const MlpParams p) 
     const uint32_t stage_d16 = (uint32_t)(stage_bytes >> 4), kblk_d16 = A_KBLOCK_BYTES >> 4;
     RingPos rp{0, 0u};
     auto gemm1 = [&](int j) {
-      const int buf = j & 1;
-      MLP_TIMED(2, mbar_wait(&sh->hacc_empty[buf], (((uint32_t)j >> 1) & 1u) ^ 1u));
+      const int buf = hacc1 ? 0 : (j & 1);
+      MLP_TIMED(2, mbar_wait(&sh->hacc_empty[buf], ((hacc1 ? (uint32_t)j : ((uint32_t)j >> 1)) & 1u) ^ 1u));
       const uint32_t d = tmem_base + (uint32_t)(hbase + buf * HC);
       for (int kb = 0; kb < KB1; ++kb) {
         MLP_TIMED(1, mbar_wait(&sh->full[rp.s], rp.ph));
@@ -236,20 +237,22 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(const MlpParams p) 
     const int cb_end = (steps2 & 1) ? steps2 : cb_beg + (steps2 >> 1);
     float v[32];
     for (int j = 0; j < nj; ++j) {
-      const int buf = j & 1;
+      const int buf = j & 1;                       // hidden smem tile
+      const int abuf = hacc1 ? 0 : buf;            // hidden accumulator in TMEM
       const uint32_t ph = ((uint32_t)j >> 1) & 1u;
+      const uint32_t aph = hacc1 ? ((uint32_t)j & 1u) : ph;
       if (warp == 2) {
-        MLP_TIMED(6, mbar_wait(&sh->hacc_full[buf], ph));
+        MLP_TIMED(6, mbar_wait(&sh->hacc_full[abuf], aph));
         MLP_TIMED(7, mbar_wait(&sh->hs_empty[buf], ph ^ 1u));
       } else {
-        mbar_wait(&sh->hacc_full[buf], ph);
+        mbar_wait(&sh->hacc_full[abuf], aph);
         mbar_wait(&sh->hs_empty[buf], ph ^ 1u);
       }
       tc_fence_after();
       const long long t_g0 = MLP_CLOCK();
       uint8_t* hrow = hs_smem + buf * nkk * A_KBLOCK_BYTES;
       const float* bj = b1s + j * HC;
-      const uint32_t t_chunk = lane_addr + (uint32_t)(hbase + buf * HC);
+      const uint32_t t_chunk = lane_addr + (uint32_t)(hbase + abuf * HC);
       for (int cb = cb_beg; cb < cb_end; cb += 2) {
         const bool two = cb + 1 < cb_end;
         tmem_ld16(t_chunk + cb * 16, v);
@@ -273,7 +276,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(const MlpParams p) 
       }
       tc_fence_before();
       fence_proxy_async();
-      mbar_arrive(&sh->hacc_empty[buf]);
+      mbar_arrive(&sh->hacc_empty[abuf]);
       mbar_arrive(&sh->hs_full[buf]);
       if (warp == 2) MLP_PROF_ADD(8, t_g0);
     }
@@ -333,7 +336,9 @@ int launch_mlp(MlpParams p, cudaStream_t stream) {
   SWN_CHECK(p.TR % 16 == 0 && p.TR >= 16 && p.TR <= 256 && C16 % p.TR == 0, "mlp: bad TR=%d for C=%d", p.TR, C);
   const int nj = (4 * C) / p.HC;
   const int KB1 = (C16 + 63) >> 6, nkk = (p.HC + 63) >> 6;
-  int cols = ((C16 + 31) & ~31) + (nj > 1 ? 2 : 1) * p.HC, tc = 32;
+  p.n_hacc = nj > 1 ? 2 : 1;
+  if (((C16 + 31) & ~31) + p.n_hacc * p.HC > 512) p.n_hacc = 1;
+  int cols = ((C16 + 31) & ~31) + p.n_hacc * p.HC, tc = 32;
   while (tc < cols) tc <<= 1;
   SWN_CHECK(tc <= 512, "mlp: TMEM overflow (C=%d HC=%d)", C, p.HC);
   p.tmem_cols = tc;
