@@ -23,11 +23,12 @@ static void mlp_config(int C, int* HC, int* TR) {
   // columns — measured 13 % faster than two 64-column accumulators: 0.60 -> 0.52 ms at M = 122 880)
   (void)hbase;
   if (C > 96 && Hd % 128 == 0) *HC = 128;
+  else if (C == 96) *HC = 96;              // persistent kernel: 4 chunks of 96 measured 5 % faster than 6 of 64
   else if (Hd % 64 == 0) *HC = 64;
   else *HC = Hd;
   *TR = C16 <= 256 ? C16 : (C16 % 128 == 0 ? 128 : C16 / 2);
   // experiment hooks (tools/bench_ops.py sweeps): SWN_MLP_HC / SWN_MLP_TR override the tiling of the C >= 192 kernel
-  if (C > 96) {
+  if (C >= 96) {
     if (const char* e = getenv("SWN_MLP_HC")) { const int v = atoi(e); if (v >= 16 && v % 16 == 0 && Hd % v == 0) *HC = v; }
     if (const char* e = getenv("SWN_MLP_TR")) { const int v = atoi(e); if (v >= 16 && v % 16 == 0 && C16 % v == 0) *TR = v; }
   }
