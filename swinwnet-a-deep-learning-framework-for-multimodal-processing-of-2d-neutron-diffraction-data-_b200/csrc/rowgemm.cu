@@ -17,6 +17,9 @@
 
 namespace swn {
 
+#ifndef SWN_RG_UNR2
+#define SWN_RG_UNR2 3
+#endif
 constexpr int RG_WARPS = 10;
 constexpr int RG_THREADS = RG_WARPS * 32;
 
@@ -80,7 +83,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) rowgemm_kernel(const RowGemmPar
 
   // ===== prologue: all warps build the resident A tile (bf16, swizzled) =====
   {
-    constexpr int UNR = KV == 1 ? 4 : (KV <= 3 ? 2 : 1);
+    constexpr int UNR = KV == 1 ? 4 : (KV == 2 ? SWN_RG_UNR2 : (KV == 3 ? 2 : 1));
     const int M = p.M;
     if (p.a_mode == A_BF16) {
       const op_t* A = reinterpret_cast<const op_t*>(p.A);

@@ -90,6 +90,11 @@ class SwinWNetInference:
         self._reset_outputs()
         with torch.no_grad():
             B = images.shape[0]
+            if B == 0:      # empty batch: empty result of the right shape, no launch (a zero-sized grid is a CUDA error)
+                Bz, Cin, H, W = images.shape
+                cout = 2 if (two_channel or Cin == 2) else Cin
+                self.images_masked_hr = torch.empty(0, cout, 2 * H, 2 * W, device=self.device, dtype=torch.float32)
+                return self.images_masked_hr
             if B <= self.max_batch:
                 out = self._run_graphed(images, two_channel) if self.cuda_graph else self._run(images, two_channel)
             else:

@@ -119,6 +119,29 @@ def test_oracle_parity_random_seed(manifest):
         assert relerr(getattr(inf, k), ref[k]) <= TOL, k
 
 
+@pytest.mark.parametrize("H,W", [(22, 18), (36, 50), (10, 130), (62, 44)])
+def test_ragged_and_tiny_geometries_against_oracle(manifest, H, W):
+    """edge geometries: grids that are no multiple of the window (5), the patch (2) or the merge (2) at some scale, and
+    images so small that the deepest stage is a single, mostly padded window — every stage against the CPU oracle."""
+    sd = O.make_state_dict(manifest["wnet_em"], seed=7)
+    m = S.SwinWNet(error_matrix=True, depths=D2)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV).eval()
+    x = O.synthetic_diffractions(2, seed=17, H=H, W=W)
+    ref = O.st_pipeline(sd, x)
+    inf = S.SwinWNetInference(m, DEV)
+    out = inf(x.to(DEV))
+    assert out.shape == ref["images_masked_hr"].shape
+    for k in ("seg_lr_logits", "upscaled_norm", "seg_hr_logits", "images_masked_hr"):
+        assert relerr(getattr(inf, k), ref[k]) <= TOL, k
+
+
+def test_empty_batch_returns_empty_result(wnet_em):
+    inf = S.SwinWNetInference(wnet_em, DEV)
+    out = inf(torch.zeros(0, 1, 250, 480, device=DEV))
+    assert out.shape == (0, 2, 500, 960)
+
+
 def test_batch_independence_and_determinism_full_size(wnet_em):
     """size-independent properties at the dataset geometry: a diffraction's result does not depend on its
     batch neighbours (how the batch is sharded over GPUs) and the path is run-to-run deterministic."""
