@@ -816,7 +816,7 @@ __global__ void __launch_bounds__(512, 1) swin_attn_stream_kernel(const FusedBlo
   issue_loads(0);
 
   // optional phase profile: thread 0 accumulates the cycles between consecutive marks
-  __shared__ long long ph_acc[PROF ? 12 : 1];
+  __shared__ long long ph_acc[PROF ? 16 : 1];
   long long ph_t = 0;
   const bool prof = PROF && tid == 0;
   auto mark = [&](int i) {
@@ -827,7 +827,7 @@ __global__ void __launch_bounds__(512, 1) swin_attn_stream_kernel(const FusedBlo
     }
   };
   if constexpr (PROF) if (prof) {
-    for (int i = 0; i < 12; ++i) ph_acc[i] = 0;
+    for (int i = 0; i < 16; ++i) ph_acc[i] = 0;
     ph_t = clock64();
   }
   int it = 0;
@@ -918,6 +918,7 @@ __global__ void __launch_bounds__(512, 1) swin_attn_stream_kernel(const FusedBlo
       for (int t = 0; t < 4; ++t, ++n_use) {
         const int wslot = n_use & 3;
         mbar_wait_spin(&bars->full[wslot], (n_use >> 2) & 1u);
+        mark(12 + t);      // profile build: time until weight tile t has landed (+ issue of the previous tile's MMAs)
         tc_fence_after();
         if (elect_one()) {
           const int ch = t >> 1, kb = t & 1;
@@ -1054,7 +1055,7 @@ __global__ void __launch_bounds__(512, 1) swin_attn_stream_kernel(const FusedBlo
     mark(7);
   }
   if constexpr (PROF) if (prof)
-    for (int i = 0; i < 12; ++i) p.phase_cycles[(long long)blockIdx.x * 16 + i] += ph_acc[i];
+    for (int i = 0; i < 16; ++i) p.phase_cycles[(long long)blockIdx.x * 16 + i] += ph_acc[i];
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, FS_TMEM);

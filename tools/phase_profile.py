@@ -28,7 +28,8 @@ if C == 96:
     Wpk, fpk = packing.pack_fused_attn_stream(*params[:7], nH)
     do_mlp = False
     names = ["load wait", "LN stats", "LN normalise", "qkv MMA", "qkv epilogue", "attention", "proj: barrier", "epilogue",
-             "proj: MMA issue", "proj: issue loads", "proj: MMA wait"]
+             "proj: MMA issue", "proj: issue loads", "proj: MMA wait", "(unused)",
+             "qkv: weight tile 0 landed", "qkv: tile 1 landed", "qkv: tile 2 landed", "qkv: tile 3 landed"]
 else:
     Wpk, fpk = packing.pack_fused_block(*params, nH)
     do_mlp = not a.attn_only
