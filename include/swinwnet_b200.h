@@ -46,6 +46,7 @@ typedef struct swn_rowgemm_args {
 
 const char* swn_last_error(void);
 int swn_abi_version(void);
+const char* swn_build_digest(void); /* sha256 of the sources + nvcc flags this library was built from (build.py) */
 int swn_sizeof_rowgemm_args(void); /* lets FFI bindings verify their struct mirror */
 int swn_operand_is_bf16(void);     /* 16-bit tensor-core operand type of this build: 0 = IEEE fp16 (default), 1 = bf16 */
 
@@ -119,9 +120,33 @@ int swn_sigmoid_mask(const float* img, int Cimg, const float* seg, float* images
 int swn_dspace_histogram(const float* img, long long img_stride, const int* bin_of_pixel, int B, int n_pixels, int n_bins,
                          float* out, void* stream);
 
+/* ensure_2ch (ST_Inference_Pipline.py:32-37): out[b,0] = x[b,0], out[b,1] = sqrt(|x[b,0]|); x [B,1,HW], out [B,2,HW]. */
+int swn_ensure_2ch(const float* x, float* out, int B, int HW, void* stream);
+
 /* normalize_piecewise (inverse=0) / denormalize_piecewise (inverse=1) (ST_Inference_Pipline.py:39-67). */
 int swn_normalize(const float* x, const float* minmax, float* out, int BC, int H, int W, float threshold, float eps,
                   int inverse, void* stream);
+
+/* ---- training side ---------------------------------------------------------------------- */
+/* One entry per parameter tensor; `g` may be null (frozen module or a branch unused in this step: the even / odd steps
+ * of FullModel_supervised_trainer.py:231-288 leave different sub-modules without gradients). */
+typedef struct swn_param_desc {
+  float* p; float* g; float* m; float* v;
+  int64_t n;          /* elements */
+  int64_t flat_off;   /* element offset of this tensor inside the flat gradient bucket */
+} swn_param_desc;
+
+/* torch.optim.AdamW step for ALL parameters in one launch (the optimizer the reference trainers build:
+ * FullModel_supervised_trainer.py:85-92): p *= 1 - lr*wd; m, v updates; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps).
+ * `table` = device array of descriptors, `chunks` = device int32 pairs (tensor index, element offset), one CTA per
+ * 4096-element chunk; gradients are multiplied by grad_scale first (1/GradScaler scale, or 1). */
+int swn_adamw_multi(const swn_param_desc* table, const int32_t* chunks, int n_chunks, double lr, double beta1, double beta2,
+                    double eps, double weight_decay, int step, double grad_scale, void* stream);
+
+/* Data-parallel gradient bucket: unpack=0 gathers every gradient (zeros where g is null) into the flat fp32 bucket that
+ * NCCL all-reduces; unpack=1 scatters flat*scale back into the gradients that exist. */
+int swn_grad_bucket_copy(const swn_param_desc* table, const int32_t* chunks, int n_chunks, float* flat, int unpack,
+                         double scale, void* stream);
 
 #ifdef __cplusplus
 }

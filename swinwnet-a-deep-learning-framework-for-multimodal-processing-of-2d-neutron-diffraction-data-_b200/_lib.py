@@ -5,9 +5,12 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libswinwnet_b200.so")
+# SWN_LIB_VARIANT selects an alternative in-tree build of the same sources (build.py: "bf16" = bf16 tensor-core
+# operands, "prof" = profiling / tuning build used by tools/); the default is the product build (fp16 operands).
+VARIANT = os.environ.get("SWN_LIB_VARIANT", "")
+LIB_PATH = os.path.join(HERE, f"libswinwnet_b200{'_' + VARIANT if VARIANT else ''}.so")
 
-c_int, c_float, c_void_p, c_longlong = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_longlong
+c_int, c_float, c_void_p, c_longlong, c_double = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_double
 
 
 class RowGemmArgs(ctypes.Structure):
@@ -27,6 +30,7 @@ class RowGemmArgs(ctypes.Structure):
 SIGNATURES = {
     "swn_last_error": (ctypes.c_char_p, []),
     "swn_abi_version": (c_int, []),
+    "swn_build_digest": (ctypes.c_char_p, []),
     "swn_sizeof_rowgemm_args": (c_int, []),
     "swn_operand_is_bf16": (c_int, []),
     "swn_mlp_config": (c_int, [c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
@@ -49,6 +53,10 @@ SIGNATURES = {
                                  c_int, c_void_p]),
     "swn_dspace_histogram": (c_int, [c_void_p, c_longlong, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "swn_normalize": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_int, c_void_p]),
+    "swn_ensure_2ch": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "swn_adamw_multi": (c_int, [c_void_p, c_void_p, c_int, c_double, c_double, c_double, c_double, c_double, c_int, c_double,
+                                c_void_p]),
+    "swn_grad_bucket_copy": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_double, c_void_p]),
 }
 
 _lib = None
@@ -68,6 +76,14 @@ def load():
             fn.restype, fn.argtypes = res, args
         if lib.swn_abi_version() != 1 or lib.swn_sizeof_rowgemm_args() != ctypes.sizeof(RowGemmArgs):
             raise RuntimeError("libswinwnet_b200.so ABI mismatch (version or swn_rowgemm_args layout)")
+        # the digest of the sources + flags is compiled into the library: a stale build must not run against newer
+        # packing / Python code (the weight images and parameter structs are defined on both sides)
+        from . import build as _build
+        if os.path.isdir(_build.CSRC) and not os.environ.get("SWN_SKIP_DIGEST_CHECK"):
+            want, have = _build.digest(VARIANT), lib.swn_build_digest().decode()
+            if want != have:
+                raise RuntimeError(f"{LIB_PATH} is stale (built from other sources/flags: {have[:12]} != {want[:12]}); "
+                                   "rebuild with `python __graft_entry__.py build`")
         _lib = lib
     return _lib
 

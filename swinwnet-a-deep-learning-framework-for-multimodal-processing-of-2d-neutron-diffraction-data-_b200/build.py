@@ -1,4 +1,13 @@
-"""Builds libswinwnet_b200.so in-tree with nvcc for sm_100a (no torch involved)."""
+"""Builds libswinwnet_b200[_<variant>].so in-tree with nvcc for sm_100a (no torch involved).
+
+Variants (selected at load time with SWN_LIB_VARIANT, see _lib.py):
+    ""      the product build: IEEE fp16 tensor-core operands, fp32 accumulation
+    "bf16"  -DSWN_OPERAND_BF16=1: bf16 operands (same kernels)
+    "prof"  -DSWN_MLP_PROFILE=1 -DSWN_TUNING_HOOKS=1: in-kernel role-wait clocks + getenv tiling overrides (tools/ only)
+
+The sha256 of the sources + flags is compiled INTO the library (swn_build_digest()); _lib.load() compares it with the
+digest of the sources it sits next to, so a stale .so can never run silently against newer packing / Python code.
+"""
 import hashlib
 import os
 import subprocess
@@ -6,37 +15,43 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libswinwnet_b200.so")
-SOURCES = ["api.cu", "rowgemm.cu", "rowgemm_persist.cu","mlp.cu", "mlp_persist.cu", "window_attn.cu", "small_block.cu", "swin_fused.cu", "cross_attn.cu", "elementwise.cu"]
+SOURCES = ["api.cu", "rowgemm.cu", "rowgemm_persist.cu", "mlp.cu", "mlp_persist.cu", "window_attn.cu", "small_block.cu",
+           "swin_fused.cu", "cross_attn.cu", "elementwise.cu", "train_ops.cu"]
 HEADERS = ["common.cuh", "kernels.h", os.path.join("..", "..", "include", "swinwnet_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+VARIANTS = {"": [], "bf16": ["-DSWN_OPERAND_BF16=1"], "prof": ["-DSWN_MLP_PROFILE=1", "-DSWN_TUNING_HOOKS=1"]}
 
 
-NVCC_FLAGS += [f for f in os.environ.get("SWN_NVCC_EXTRA", "").split() if f]   # e.g. -DSWN_MLP_PROFILE=1 (profiling builds)
+def lib_path(variant=""):
+    return os.path.join(HERE, f"libswinwnet_b200{'_' + variant if variant else ''}.so")
 
 
-def _digest():
+def flags(variant=""):
+    extra = [f for f in os.environ.get("SWN_NVCC_EXTRA", "").split() if f]   # ad-hoc experiment flags
+    return NVCC_FLAGS + VARIANTS[variant] + extra
+
+
+def digest(variant=""):
     h = hashlib.sha256()
     for f in SOURCES + HEADERS:
         with open(os.path.join(CSRC, f), "rb") as fh:
             h.update(fh.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(flags(variant)).encode())
     return h.hexdigest()
 
 
-def build(force=False, verbose=False):
-    stamp = LIB + ".stamp"
-    dig = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
-        return LIB
+def build(force=False, verbose=False, variant=""):
+    lib, stamp, dig = lib_path(variant), lib_path(variant) + ".stamp", digest(variant)
+    if not force and os.path.exists(lib) and os.path.exists(stamp) and open(stamp).read() == dig:
+        return lib
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    objs = []
-    procs = []
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    objs, procs = [], []
+    bdir = os.path.join(HERE, "build", variant or "default")
+    os.makedirs(bdir, exist_ok=True)
     for src in SOURCES:
-        obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(bdir, src.replace(".cu", ".o"))
+        cmd = [nvcc, *flags(variant), f'-DSWN_BUILD_DIGEST="{dig}"', "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -49,11 +64,13 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    subprocess.check_call([nvcc, "-shared", "-o", LIB, *objs, "-lcudart"])
-    with open(stamp, "w") as f:
+    subprocess.check_call([nvcc, "-shared", "-o", lib, *objs, "-lcudart"])
+    with open(stamp, "w") as f:   # fast path only (git-ignored); the authoritative check is swn_build_digest()
         f.write(dig)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    v = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--variant=")]
+    for variant in (v or [""]):
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, variant=variant))

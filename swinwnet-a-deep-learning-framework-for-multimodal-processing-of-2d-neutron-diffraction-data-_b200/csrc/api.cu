@@ -1,9 +1,13 @@
 // extern "C" boundary of libswinwnet_b200.so (declared in include/swinwnet_b200.h).
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 
 #include "../../include/swinwnet_b200.h"
+#ifndef SWN_TUNING_HOOKS
+#define SWN_TUNING_HOOKS 0
+#endif
 #include "common.cuh"
 #include "kernels.h"
 
@@ -27,20 +31,26 @@ static void mlp_config(int C, int* HC, int* TR) {
   else if (Hd % 64 == 0) *HC = 64;
   else *HC = Hd;
   *TR = C16 <= 256 ? C16 : (C16 % 128 == 0 ? 128 : C16 / 2);
-  // experiment hooks (tools/bench_ops.py sweeps): SWN_MLP_HC / SWN_MLP_TR override the tiling of the C >= 192 kernel
+#if SWN_TUNING_HOOKS
+  // tuning build only (build.py variant "prof", tools/bench_ops.py sweeps): SWN_MLP_HC / SWN_MLP_TR override the tiling
   if (C >= 96) {
     if (const char* e = getenv("SWN_MLP_HC")) { const int v = atoi(e); if (v >= 16 && v % 16 == 0 && Hd % v == 0) *HC = v; }
     if (const char* e = getenv("SWN_MLP_TR")) { const int v = atoi(e); if (v >= 16 && v % 16 == 0 && C16 % v == 0) *TR = v; }
   }
+#endif
 }
 static long long* g_phase_cycles = nullptr;
 static int mlp_persist_max_c() {
+#if SWN_TUNING_HOOKS
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("SWN_MLP_PERSIST_MAX_C");
-    v = e ? atoi(e) : 96;   // the DIRECT variant (C = 192) is correct but measured 9 % slower than mlp.cu so far: opt-in
+    v = e ? atoi(e) : 96;
   }
   return v;
+#else
+  return 96;   // the DIRECT variant (C = 192) is correct but measured 9 % slower than mlp.cu so far
+#endif
 }
 static int num_sms() {
   static int n = 0;
@@ -59,6 +69,10 @@ extern "C" {
 
 const char* swn_last_error(void) { return g_err; }
 int swn_abi_version(void) { return SWN_ABI_VERSION; }
+#ifndef SWN_BUILD_DIGEST
+#define SWN_BUILD_DIGEST "unknown"
+#endif
+const char* swn_build_digest(void) { return SWN_BUILD_DIGEST; }
 int swn_sizeof_rowgemm_args(void) { return (int)sizeof(swn_rowgemm_args); }
 int swn_operand_is_bf16(void) { return SWN_OPERAND_BF16; }
 
@@ -184,10 +198,32 @@ int swn_dspace_histogram(const float* img, long long img_stride, const int* bin_
   return launch_dspace_hist(img, img_stride, bin_of_pixel, B, n_pixels, n_bins, out, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int swn_ensure_2ch(const float* x, float* out, int B, int HW, void* stream) {
+  SWN_CHECK(x && out && B > 0 && HW > 0, "ensure_2ch: bad arguments");
+  return launch_ensure_2ch(x, out, B, HW, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int swn_normalize(const float* x, const float* minmax, float* out, int BC, int H, int W, float threshold, float eps,
                   int inverse, void* stream) {
   SWN_CHECK(x && minmax && out, "normalize: null pointer");
   return launch_normalize(x, minmax, out, BC, H, W, threshold, eps, inverse, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int swn_adamw_multi(const swn_param_desc* table, const int32_t* chunks, int n_chunks, double lr, double beta1, double beta2,
+                    double eps, double weight_decay, int step, double grad_scale, void* stream) {
+  SWN_CHECK(table && chunks && n_chunks > 0 && step >= 1, "adamw_multi: bad arguments");
+  static_assert(sizeof(swn_param_desc) == sizeof(AdamWTensor), "swn_param_desc layout");
+  const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+  return launch_adamw_multi(reinterpret_cast<const AdamWTensor*>(table), reinterpret_cast<const int2*>(chunks), n_chunks, (float)lr,
+                            (float)beta1, (float)beta2, (float)eps, (float)weight_decay, (float)bc1, (float)sqrt(bc2), (float)grad_scale,
+                            reinterpret_cast<cudaStream_t>(stream));
+}
+
+int swn_grad_bucket_copy(const swn_param_desc* table, const int32_t* chunks, int n_chunks, float* flat, int unpack, double scale,
+                         void* stream) {
+  SWN_CHECK(table && chunks && flat && n_chunks > 0, "grad_bucket_copy: bad arguments");
+  return launch_bucket_copy(reinterpret_cast<const AdamWTensor*>(table), reinterpret_cast<const int2*>(chunks), n_chunks, flat,
+                            unpack ? 1 : 0, (float)scale, reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

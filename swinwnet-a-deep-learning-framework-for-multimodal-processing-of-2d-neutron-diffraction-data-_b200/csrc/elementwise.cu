@@ -466,6 +466,35 @@ int launch_sigmoid_mask(const float* img, int Cimg, const float* seg, float* ima
   return 0;
 }
 
+// ensure_2ch: [B,1,HW] -> [B,2,HW], channel 1 = sqrt(|channel 0|)
+__global__ void ensure_2ch_kernel(const float* __restrict__ x, float* __restrict__ out, int HW) {
+  const int b = blockIdx.y;
+  const float* src = x + (long long)b * HW;
+  float* d0 = out + (long long)b * 2 * HW;
+  float* d1 = d0 + HW;
+  if ((HW & 3) == 0) {
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4; i < HW; i += gridDim.x * blockDim.x * 4) {
+      const float4 v = *reinterpret_cast<const float4*>(src + i);
+      *reinterpret_cast<float4*>(d0 + i) = v;
+      *reinterpret_cast<float4*>(d1 + i) = make_float4(sqrtf(fabsf(v.x)), sqrtf(fabsf(v.y)), sqrtf(fabsf(v.z)), sqrtf(fabsf(v.w)));
+    }
+  } else {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+      const float v = src[i];
+      d0[i] = v;
+      d1[i] = sqrtf(fabsf(v));
+    }
+  }
+}
+int launch_ensure_2ch(const float* x, float* out, int B, int HW, cudaStream_t st) {
+  int bx = (HW / 4 + 255) / 256;
+  if (bx > 64) bx = 64;
+  if (bx < 1) bx = 1;
+  ensure_2ch_kernel<<<dim3(bx, B), 256, 0, st>>>(x, out, HW);
+  SWN_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // normalize_piecewise / denormalize_piecewise; minmax is [B*C][2]
 __global__ void normalize_kernel(const float* __restrict__ x, const float* __restrict__ minmax, float* __restrict__ out,
                                  int HW, float thr, float eps, int inverse) {

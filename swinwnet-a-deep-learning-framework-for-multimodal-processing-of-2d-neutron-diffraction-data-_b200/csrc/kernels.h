@@ -124,7 +124,21 @@ int launch_sigmoid_mask(const float* img, int Cimg, const float* seg, float* ima
                         float* minmax, int B, int Cout, int H, int W, cudaStream_t s);
 int launch_dspace_hist(const float* img, long long img_stride, const int* bin_of_pixel, int B, int n_pix, int n_bins,
                        float* out, cudaStream_t s);
+int launch_ensure_2ch(const float* x, float* out, int B, int HW, cudaStream_t s);
 int launch_normalize(const float* x, const float* minmax, float* out, int BC, int H, int W, float thr, float eps,
                      int inverse, cudaStream_t s);
+
+// ---- train_ops.cu ---------------------------------------------------------------------------
+struct AdamWTensor {      // mirror of swn_param_desc (include/swinwnet_b200.h)
+  float* p;               // parameter (fp32 master, updated in place)
+  float* g;               // gradient or null (frozen / unused this step)
+  float* m;               // exp_avg
+  float* v;               // exp_avg_sq
+  long long n;            // elements
+  long long flat_off;     // element offset inside the flat all-reduce bucket
+};
+int launch_adamw_multi(const AdamWTensor* tab, const int2* chunks, int n_chunks, float lr, float beta1, float beta2, float eps,
+                       float wd, float bc1, float bc2_sqrt, float grad_scale, cudaStream_t s);
+int launch_bucket_copy(const AdamWTensor* tab, const int2* chunks, int n_chunks, float* flat, int mode, float scale, cudaStream_t s);
 
 }  // namespace swn

@@ -31,20 +31,22 @@ class SwinWNetInference:
         for k in self._STAGES:
             setattr(self, k, None)
 
-    # kept for API parity with the reference's static helpers (they run the same kernels)
+    # same static helper as the reference (ST_Inference_Pipline.py:32-37): works on any device; on CUDA it is one
+    # vectorised kernel (swn_ensure_2ch) instead of abs + sqrt + cat
     @staticmethod
     def ensure_2ch(x):
         if x.size(1) == 2:
             return x
-        z = torch.zeros(x.size(0), 1, x.size(2), x.size(3), device=x.device)
-        images, _, _, _ = ops.sigmoid_mask(x.float().contiguous(), z, ensure_2ch=True, want_minmax=False)
-        return images
+        if x.is_cuda and x.size(1) == 1:
+            return ops.ensure_2ch(x.float().contiguous())
+        return torch.cat([x, torch.sqrt(torch.abs(x))], dim=1)
 
     def _run(self, images, two_channel=True):
         m = self.model
         images = images.to(self.device).float().contiguous()
-        seg, skips_seg = m.segment_1(self.ensure_2ch(images) if two_channel else images)
-        images2, seg_map_lr, masked_lr, minmax = ops.sigmoid_mask(images, seg, ensure_2ch=two_channel, want_minmax=True)
+        images2 = self.ensure_2ch(images) if two_channel else images      # computed once, reused by the mask stage
+        seg, skips_seg = m.segment_1(images2)
+        _, seg_map_lr, masked_lr, minmax = ops.sigmoid_mask(images2, seg, ensure_2ch=False, want_minmax=True)
         norm = ops.normalize(masked_lr, minmax, inverse=False)
         upscaled_norm, skips_sr = m.upscale(norm, skips_seg)
         upscaled_denorm = ops.normalize(upscaled_norm, minmax, inverse=True)
@@ -98,8 +100,16 @@ class SwinWNetInference:
             if B <= self.max_batch:
                 out = self._run_graphed(images, two_channel) if self.cuda_graph else self._run(images, two_channel)
             else:
-                parts = [self._run(images[i:i + self.max_batch], two_channel) for i in range(0, B, self.max_batch)]
-                out = {k: torch.cat([p[k] for p in parts], 0) for k in parts[0]}
+                # micro-batches write into outputs allocated once (no torch.cat: at B = 4096 the ten stage tensors are
+                # ~20 MB per diffraction, and a concatenation would hold them twice)
+                out = None
+                for lo in range(0, B, self.max_batch):
+                    part = self._run(images[lo:lo + self.max_batch], two_channel)
+                    if out is None:
+                        out = {k: torch.empty((B,) + tuple(v.shape[1:]), device=v.device, dtype=v.dtype) for k, v in part.items()}
+                    for k, v in part.items():
+                        out[k][lo:lo + v.shape[0]].copy_(v)
+                    del part
             for k, v in out.items():
                 setattr(self, k, v)
         return self.images_masked_hr
@@ -119,29 +129,49 @@ class SwinWNetInference:
         B, Cin, H, W = images.shape
         cout = 2 if (two_channel or Cin == 2) else Cin
         if out is None:
-            out = torch.empty(B, cout, 2 * H, 2 * W, dtype=torch.float32).pin_memory()
-        h2d.wait_stream(main)            # the caller may still be producing `images` / consuming device buffers
+            out = torch.empty(B, cout, 2 * H, 2 * W, dtype=torch.float32)
+            out = out.pin_memory() if B else out
         self._reset_outputs()
+        self.host_done = torch.cuda.Event()
+        if B == 0:                       # nothing to launch (a zero-sized grid is a CUDA error)
+            self.images_masked_hr = torch.empty(0, cout, 2 * H, 2 * W, device=dev, dtype=torch.float32)
+            self.host_done.record(main)
+            return out
+        h2d.wait_stream(main)            # the caller may still be producing `images` / consuming device buffers
         with torch.no_grad():
-            staged = []
-            for lo in range(0, B, chunk):      # all input copies are queued up front (0.96 MB per diffraction)
+            # at most IN_FLIGHT input chunks are resident on the device: chunk i+2 is copied only after chunk i has been
+            # consumed (0.96 MB per diffraction; an up-front copy of B = 4096 would pin 4 GB of workspace)
+            IN_FLIGHT = 2
+            los = list(range(0, B, chunk))
+            staged, consumed = {}, {}
+
+            def stage(i):
                 with torch.cuda.stream(h2d):
-                    xd = images[lo:lo + chunk].to(dev, non_blocking=True)
+                    if i - IN_FLIGHT in consumed:
+                        h2d.wait_event(consumed.pop(i - IN_FLIGHT))
+                    xd = images[los[i]:los[i] + chunk].to(dev, non_blocking=True)
                     ev = torch.cuda.Event()
                     ev.record(h2d)
-                staged.append((lo, xd, ev))
-            for lo, xd, ev in staged:
+                staged[i] = (xd, ev)
+            for i in range(min(IN_FLIGHT, len(los))):
+                stage(i)
+            res = None
+            for i, lo in enumerate(los):
+                xd, ev = staged.pop(i)
                 main.wait_event(ev)
                 xd.record_stream(main)
                 res = self._run(xd, two_channel)
                 done = torch.cuda.Event()
                 done.record(main)
+                consumed[i] = done
+                if i + IN_FLIGHT < len(los):
+                    stage(i + IN_FLIGHT)
                 with torch.cuda.stream(d2h):
                     d2h.wait_event(done)
                     out[lo:lo + xd.shape[0]].copy_(res["images_masked_hr"], non_blocking=True)
                 res["images_masked_hr"].record_stream(d2h)
+                del xd
             for k, v in res.items():
                 setattr(self, k, v)
-            self.host_done = torch.cuda.Event()
             self.host_done.record(d2h)
         return out
