@@ -6,11 +6,18 @@ ST_Inference_Pipline.py:73-136) over one batch of synthetic diffractions of the 
 [B,1,250,480] (error channel derived -> multimodal [B,2,250,480] model, BASELINE configs[1], batch 64
 per GPU).  N>1: every rank runs its own batch shard (weak scaling, no data-path collective).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--config 1|2|3|4] [--impl b200|reference]
 
 Prints ONE JSON line (rank 0).  `value` = device-resident inputs; `e2e` = pinned host inputs + D2H of the
-result inside the timed region, through the public SwinWNetInference call.  `--impl reference` times the
-oracle (CPU port of the reference, all host threads) on a bounded sample.
+result inside the timed region, through the public SwinWNetInference call.  Every kernel family is timed with CUDA
+events inside the timed region (`kernels`, shares sum to ~1); `roofline` is the family with the largest share.
+`parity_check`: samples 0 and B-1 of the timed batch against the fp32 oracle and against a solo B=1 run (bit-equal);
+the process exits non-zero when it fails.  `library_bar`: the unmodified reference (baseline/_ref) on the same GPU in
+eager fp32 / TF32 / bf16-autocast.  `--impl reference` times the unmodified reference's CPU forward (all host
+threads, bounded sample); if it is not staged, the oracle port (kind "port").
+
+--config: 2 (default) = BASELINE configs[1]; 1 = diffraction-only model, manual three-call pipeline; 3 = the
+single-branch SwinUNet / SwinUNetSR at batch 256; 4 = multimodal batch sweep 1..4096 (micro-batched above 64).
 """
 import argparse
 import json
@@ -24,6 +31,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 H, W = 250, 480
 DEPTHS = [2, 2, 2, 2]
@@ -40,9 +48,10 @@ def peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per step of the kernel family, summed over its launches, from the
-# `ncu --set full` captures summarised under profiles/ (null = not captured for this build)
-TRAFFIC_NCU = {"fused": 22.7e9, "mlp": None}   # bytes per step (22 launches at batch 64), profiles/r1_ncu_fused_*.txt
+def traffic_table():
+    """dram bytes per step and kernel family from the committed ncu captures (tools/ncu_traffic.py regenerates it)."""
+    p = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    return json.load(open(p)) if os.path.exists(p) else {}
 
 
 def shard_bounds(n_items, rank, world):
@@ -94,35 +103,228 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def run_reference(args, rank):
-    """the reference's own algorithm on the host CPU (oracle port; the Python reference cannot travel)."""
-    if rank != 0:
-        return
-    from oracle import swinwnet_oracle as O
+# =====================================================================================================================
+# reference arm / CPU baseline
+# =====================================================================================================================
+def cpu_reference_rate(steps, warm, sample_b=1):
+    """the reference's own CPU forward (unmodified modules from baseline/_ref or /root/reference when staged, else the
+    oracle port) through its public API, all host threads, `sample_b` diffractions per step."""
+    import benchdata
     man = json.load(open(os.path.join(ROOT, "tests", "golden", "manifest.json")))
-    sd = O.make_state_dict(man["wnet_em"], seed=1)
+    sd = benchdata.make_state_dict(man["wnet_em"], seed=1)
     cores = os.cpu_count()
     torch.set_num_threads(cores)
-    sample_b = 1                                                  # bounded sample: 1 diffraction per step
-    x = O.synthetic_diffractions(sample_b, seed=0, two_channel=False)
-    steps, warm = min(args.steps, 6), min(args.warmup, 1)
+    x = benchdata.synthetic_diffractions(sample_b, seed=0, two_channel=False)
+    try:
+        from stage_reference import import_reference
+        _, R, P = import_reference()
+        model = R.SwinWNet(error_matrix=True, depths=DEPTHS)
+        model.load_state_dict(sd, strict=True)
+        inf = P.SwinWNetInference(model, "cpu")
+        fn, kind = (lambda: inf(x)), "reference"
+    except Exception:
+        from oracle import swinwnet_oracle as O
+        fn, kind = (lambda: O.st_pipeline(sd, x)), "port"
     with torch.no_grad():
         for _ in range(warm):
-            O.st_pipeline(sd, x)
+            fn()
         t0 = time.perf_counter()
         for _ in range(steps):
-            O.st_pipeline(sd, x)
+            fn()
         dt = (time.perf_counter() - t0) / steps
-    v = sample_b / dt
+    what = "unmodified reference SwinWNetInference (baseline/_ref)" if kind == "reference" else "fp32 torch CPU oracle port"
+    return sample_b / dt, dt, {"value": sample_b / dt, "unit": UNIT, "cores": cores, "kind": kind,
+                               "sample": f"{steps} steps x {sample_b} diffraction of the same workload, {what}, fp32"}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    steps, warm = min(args.steps, 6), min(max(args.warmup, 1), 1)
+    v, dt, cb = cpu_reference_rate(steps, warm)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "SwinWNet multimodal ST pipeline [B,2,250,480], depths [2,2,2,2], random-init weights",
-                       "sample_batch": sample_b},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{steps} steps x {sample_b} diffraction, fp32 torch CPU oracle"},
+            "config": {"workload": "SwinWNet multimodal ST pipeline [B,2,250,480] (configs[1]), depths [2,2,2,2], random-init weights",
+                       "sample_batch": 1},
+            "cpu_baseline": cb,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def library_bar(dev, batches=(8, 64), iters=3):
+    """the unmodified reference on THIS GPU (eager ATen / cuBLAS): the bar a hand-written path has to clear."""
+    try:
+        import library_bar as LB
+        r = LB.measure(batches=batches, modes=("fp32", "tf32", "bf16_autocast"), iters=iters, device=str(dev))
+    except Exception as e:
+        return {"unavailable": f"{type(e).__name__}: {str(e)[:160]}"}
+    best = {}
+    for run in r["runs"]:
+        if "diffractions_per_s" in run:
+            k = run["mode"]
+            if k not in best or run["diffractions_per_s"] > best[k]["diffractions_per_s"]:
+                best[k] = {"diffractions_per_s": run["diffractions_per_s"], "batch": run["batch"], "ms_per_call": run["ms_per_call"]}
+    return {"what": "unmodified reference SwinWNetInference on this GPU, eager", "unit": UNIT, "best": best, "runs": r["runs"]}
+
+
+# =====================================================================================================================
+# kernel-family accounting: every C-ABI op is bracketed by CUDA events; algorithmic FLOPs / bytes per call
+# =====================================================================================================================
+FAMILIES = {
+    "fused": "swn::swin_fused_kernel + swin_attn_stream_kernel (fused LN1+qkv+W-MSA+proj[+LN2+MLP], C<=96)",
+    "mlp": "swn::mlp_kernel + mlp_persist_kernel (fused LN2+fc1+GELU+fc2+residual, C>=96)",
+    "rowgemm": "swn::rowgemm_kernel + rowgemm_persist_kernel (LN/merge/convert prologue + GEMM + bias/residual/expand epilogue)",
+    "window_attn": "swn::window_attn_kernel (W-MSA core on materialised qkv, C>=192)",
+    "cross_attn": "swn::cross_attn_kernel (flash-style global MHA core)",
+    "heads": "swn::patch_embed_kernel + conv_head_mma_kernel + bilinear_up_kernel",
+    "glue": "swn::copy_cols / sigmoid_mask / normalize / ensure_2ch kernels",
+}
+OP_FAMILY = {"swin_block_fused": "fused", "swin_block_small": "fused", "mlp": "mlp", "rowgemm": "rowgemm",
+             "window_attention": "window_attn", "cross_attention": "cross_attn", "patch_embed": "heads", "seg_head": "heads",
+             "recon_head": "heads", "copy_cols": "glue", "sigmoid_mask": "glue", "normalize": "glue", "ensure_2ch": "glue"}
+
+
+def op_work(name, a, k):
+    """(algorithmic FLOPs, algorithmic HBM bytes) of one C-ABI call, from its arguments"""
+    if name == "swin_block_fused":
+        x, out, Bn, Hn, Wn, C, nH = a[:7]
+        do_mlp = a[10] if len(a) > 10 else k.get("do_mlp", True)
+        M = Bn * Hn * Wn
+        return ((24.0 if do_mlp else 8.0) * C * C + 100.0 * C) * M, 8.0 * M * C
+    if name == "swin_block_small":
+        x, out, Bn, Hn, Wn, C = a[:6]
+        M = Bn * Hn * Wn
+        return (24.0 * C * C + 100.0 * C) * M, 8.0 * M * C
+    if name == "mlp":
+        M, C = a[2], a[3]
+        return 16.0 * M * C * C, 8.0 * M * C
+    if name == "rowgemm":
+        M, K, N = k["M"], k["K"], k["nchunks"] * k["n_valid"]
+        a_bytes = M * K * (2 if k["a_mode"] == 2 else 4)
+        o_bytes = M * N * (2 if k["e_mode"] == 0 else 4)
+        r_bytes = M * N * 4 if k.get("res") is not None else 0
+        return 2.0 * M * K * N, float(a_bytes + o_bytes + r_bytes)
+    if name == "window_attention":
+        B, Hn, Wn, C = a[4], a[5], a[6], a[7]
+        M = B * Hn * Wn
+        return 100.0 * M * C, 8.0 * M * C
+    if name == "cross_attention":
+        B, Lq, Lk, C = a[3], a[4], a[5], a[6]
+        return 4.0 * B * Lq * Lk * C, 2.0 * (2 * B * Lq * C + 2 * B * Lk * C)
+    if name == "patch_embed":
+        x, out = a[0], a[5]
+        return 2.0 * out.numel() * 4 * x.shape[1], 4.0 * (x.numel() + out.numel())
+    if name == "seg_head":
+        tok, out = a[0], a[6]
+        return 2.0 * tok.shape[0] * tok.shape[1] * (9 * 48 * 24 + 24), 4.0 * (tok.numel() + out.numel())
+    if name == "recon_head":
+        tok, out = a[0], a[5]
+        return 2.0 * tok.shape[0] * tok.shape[1] * (9 * 12 * 12 + 12 * out.shape[1]), 4.0 * (tok.numel() + out.numel())
+    if name == "copy_cols":
+        return 0.0, 8.0 * a[5] * a[6]
+    if name == "sigmoid_mask":
+        img = a[0]
+        cout = 2 if (k.get("ensure_2ch") and img.shape[1] != 2) else img.shape[1]
+        n = img.shape[0] * img.shape[2] * img.shape[3]
+        return 0.0, 4.0 * n * (img.shape[1] + 1 + cout + 1)
+    if name in ("normalize", "ensure_2ch"):
+        return 0.0, 4.0 * a[0].numel() * (2 if name == "normalize" else 3)
+    return 0.0, 0.0
+
+
+class FamilyTimer:
+    def __init__(self, ops):
+        self.ops, self.orig, self.fam = ops, {}, {f: {"ev": [], "flop": 0.0, "bytes": 0.0} for f in FAMILIES}
+
+    def install(self):
+        for name, famname in OP_FAMILY.items():
+            fn = getattr(self.ops, name)
+            self.orig[name] = fn
+            setattr(self.ops, name, self._wrap(name, fn, self.fam[famname]))
+
+    def remove(self):
+        for name, fn in self.orig.items():
+            setattr(self.ops, name, fn)
+
+    @staticmethod
+    def _wrap(name, fn, f):
+        def timed_op(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a, **k)
+            e1.record()
+            fl, by = op_work(name, a, k)
+            f["ev"].append((e0, e1))
+            f["flop"] += fl
+            f["bytes"] += by
+            return r
+        return timed_op
+
+    def summary(self, steps, ms_step, pk):
+        kern = {}
+        for name, label in FAMILIES.items():
+            f = self.fam[name]
+            if not f["ev"]:
+                continue
+            k_ms = sum(a.elapsed_time(b) for a, b in f["ev"]) / steps
+            tf = f["flop"] / steps / (k_ms / 1e3) / 1e12 if k_ms > 0 else 0.0
+            gbs = f["bytes"] / steps / (k_ms / 1e3) / 1e9 if k_ms > 0 else 0.0
+            kern[name] = {"kernel": label, "launches_per_step": len(f["ev"]) // max(steps, 1), "kernel_ms_per_step": k_ms,
+                          "kernel_share_of_step": k_ms / ms_step, "achieved_tflops": tf, "tensor_frac": tf / pk["tf_sust"],
+                          "achieved_gbs": gbs, "hbm_frac": gbs / pk["hbm"],
+                          "flop_per_step": f["flop"] / steps, "bytes_per_step": f["bytes"] / steps}
+        return kern
+
+
+def roofline_of(kern, pk, traffic):
+    dom = max(kern, key=lambda n: kern[n]["kernel_ms_per_step"])
+    kd = kern[dom]
+    ridge = pk["tf_sust"] * 1e12 / (pk["hbm"] * 1e9)
+    intensity = kd["flop_per_step"] / max(kd["bytes_per_step"], 1.0)
+    hbm_bound = intensity < ridge
+    tr = traffic.get(dom, {}) if isinstance(traffic.get(dom), dict) else {}
+    per_launch = kd["launches_per_step"] or 1
+    return {"bound": "hbm" if hbm_bound else "tensor", "kernel": kd["kernel"], "family": dom,
+            "achieved": kd["achieved_gbs"] if hbm_bound else kd["achieved_tflops"],
+            "peak": pk["hbm"] if hbm_bound else pk["tf_sust"], "unit": "GB/s" if hbm_bound else "TFLOP/s",
+            "frac": kd["hbm_frac"] if hbm_bound else kd["tensor_frac"],
+            "traffic": (tr["dram_bytes_per_step"] / per_launch) if "dram_bytes_per_step" in tr else None,
+            "algorithmic_bytes_per_launch": kd["bytes_per_step"] / per_launch,
+            "algorithmic_flop_per_launch": kd["flop_per_step"] / per_launch,
+            "avg_launch_ms": kd["kernel_ms_per_step"] / per_launch,
+            "traffic_source": tr.get("source"),
+            "peak_source": pk["src"] + (" (copy bandwidth)" if hbm_bound else " (sustained bf16)"),
+            "intensity_flop_per_byte": intensity, "ridge_flop_per_byte": ridge,
+            "kernel_ms_per_step": kd["kernel_ms_per_step"], "kernel_share_of_step": kd["kernel_share_of_step"],
+            "tensor_tflops": kd["achieved_tflops"], "tensor_frac": kd["tensor_frac"],
+            "hbm_gbs": kd["achieved_gbs"], "hbm_frac": kd["hbm_frac"]}
+
+
+# =====================================================================================================================
+def parity_check(inf, x_dev, sd, two_channel=True):
+    """samples 0 and B-1 of the benchmarked batch: (1) against the fp32 CPU oracle (max-norm relative error of the logits,
+    the upscaled image and the final output, gate 2e-2); (2) against a solo B=1 run of the same sample (bit-equal)."""
+    from oracle import swinwnet_oracle as O
+    B = x_dev.shape[0]
+    full = inf(x_dev)
+    keys = ("seg_lr_logits", "upscaled_norm", "seg_hr_logits", "images_masked_hr")
+    got = {k: getattr(inf, k).clone() for k in keys}
+    idx = sorted({0, B - 1})
+    worst, bit_equal, per = 0.0, True, {}
+    with torch.no_grad():
+        for i in idx:
+            ref = O.st_pipeline(sd, x_dev[i:i + 1].cpu(), two_channel=two_channel)
+            for k in keys:
+                a, b = got[k][i:i + 1].float().cpu(), ref[k]
+                e = (a - b).abs().max().item() / max(b.abs().max().item(), 1e-6)
+                per[f"{k}[{i}]"] = e
+                worst = max(worst, e if torch.isfinite(a).all() else float("inf"))
+            solo = inf(x_dev[i:i + 1], two_channel) if not two_channel else inf(x_dev[i:i + 1])
+            bit_equal &= bool(torch.equal(solo, got["images_masked_hr"][i:i + 1]))
+    del full
+    return {"samples": idx, "max_rel": worst, "tol": 2e-2, "bit_equal_vs_solo": bit_equal, "per_tensor": per,
+            "ok": bool(worst <= 2e-2 and bit_equal)}
 
 
 def main():
@@ -130,9 +332,12 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=64, help="diffractions per GPU per step")
+    ap.add_argument("--batch", type=int, default=None, help="diffractions per GPU per step (default 64; 256 for --config 3)")
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-library-bar", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--graph", action="store_true", help="also time CUDA-graph replay of the pipeline (matters at small --batch, where a pass is launch-bound); reported under \"graph\"")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -154,45 +359,11 @@ def main():
 
     man = json.load(open(os.path.join(ROOT, "tests", "golden", "manifest.json")))
     import benchdata                               # seeded synthetic inputs / weights (no model math)
-    model = S.SwinWNet(error_matrix=True, depths=DEPTHS)
-    model.load_state_dict(benchdata.make_state_dict(man["wnet_em"], seed=1), strict=True)
-    inf = S.SwinWNetInference(model, dev, max_batch=64)
-    inf_fast = S.SwinWNetInference(model, dev, max_batch=64, cuda_graph=True) if args.graph else inf
-    B = args.batch
-    base = benchdata.synthetic_diffractions(min(B, 8), seed=100 + rank, two_channel=False)
-    x_host = base.repeat((B + base.shape[0] - 1) // base.shape[0], 1, 1, 1)[:B].contiguous()
-    x_host = (x_host * (1.0 + 0.01 * torch.arange(B).view(B, 1, 1, 1))).pin_memory()
-    x_dev = x_host.to(dev)
-    out_host = torch.empty(B, 2, 2 * H, 2 * W).pin_memory()
+    cfg = args.config
+    B = args.batch or (256 if cfg == 3 else 64)
+    two_channel = cfg != 1
+    key = {1: "wnet", 2: "wnet_em", 4: "wnet_em"}.get(cfg)
     W_ = max(args.warmup, 3)
-
-    # ---- per-kernel-family timing hooks (CUDA events on the launching stream, inside the timed region) ----
-    # fused = swn::swin_fused_kernel / swin_attn_stream_kernel (W-MSA [+ MLP] in one tcgen05 kernel, C <= 96),
-    # mlp   = swn::mlp_kernel / mlp_persist_kernel (LN + fc1 + GELU + fc2 + residual, C >= 96)
-    fam = {"fused": {"ev": [], "flop": 0.0, "bytes": 0.0}, "mlp": {"ev": [], "flop": 0.0, "bytes": 0.0}}
-    orig = {"fused": ops.swin_block_fused, "mlp": ops.mlp}
-
-    def hook(name, work):
-        fn = orig[name]
-
-        def timed_op(*a, **k):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            fn(*a, **k)
-            e1.record()
-            fl, by = work(*a, **k)
-            fam[name]["ev"].append((e0, e1))
-            fam[name]["flop"] += fl
-            fam[name]["bytes"] += by
-        return timed_op
-
-    def fused_work(x, out, Bn, Hn, Wn, C, nH, eps, Wpk, fpk, do_mlp=True):
-        M = Bn * Hn * Wn      # algorithmic FLOPs of a block: 24 C^2 + 100 C per token (8 C^2 + 100 C for the W-MSA half)
-        return ((24.0 if do_mlp else 8.0) * C * C + 100.0 * C) * M, 8.0 * M * C
-
-    def mlp_work(x, out, M, C, *a, **k):
-        return 16.0 * M * C * C, 8.0 * M * C
-    hooks = {"fused": hook("fused", fused_work), "mlp": hook("mlp", mlp_work)}
 
     def barrier():
         torch.cuda.synchronize()
@@ -210,54 +381,105 @@ def main():
         barrier()
         return max_over_ranks(e0.elapsed_time(e1), dist, dev)
 
+    def make_inputs(n):
+        base = benchdata.synthetic_diffractions(min(n, 8), seed=100 + rank, two_channel=False)
+        xh = base.repeat((n + base.shape[0] - 1) // base.shape[0], 1, 1, 1)[:n].contiguous()
+        return (xh * (1.0 + (0.01 * torch.arange(n).view(n, 1, 1, 1)) % 1.28)).pin_memory()
+
+    pk = peaks()
+    if cfg == 3:
+        # single-branch models (pretrain checkpoints' architectures), batch 256: two workloads, two numbers
+        x_host = make_inputs(B)
+        x_dev = (x_host / x_host.amax(dim=(2, 3), keepdim=True)).to(dev)
+        res = {}
+        for name, cls, gflop in (("SwinUNet", S.SwinUNet, 63.18), ("SwinUNetSR", S.SwinUNetSR, 72.73)):
+            m = cls(depths=DEPTHS)
+            m.load_state_dict(benchdata.make_state_dict(man["unet" if name == "SwinUNet" else "unetsr"], seed=1), strict=True)
+            m = m.to(dev).eval()
+
+            def step(m=m):
+                with torch.no_grad():
+                    for lo in range(0, B, 64):
+                        m(x_dev[lo:lo + 64])
+            for _ in range(W_):
+                step()
+            ms = timed(step, args.steps)
+            v = whole_job_rate(B, world, args.steps, ms)
+            res[name] = {"value": v, "unit": UNIT, "ms_per_step": ms / args.steps, "model_tflops": gflop * v / 1e3}
+        line = {"metric": METRIC, "value": res["SwinUNet"]["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": W_, "ms_per_step": res["SwinUNet"]["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16" if ops.operand_dtype() == torch.bfloat16 else "fp16", "data": "synthetic",
+                "config": {"workload": "configs[2]: SwinUNet (value) and SwinUNetSR single-branch forwards [B,1,250,480], "
+                                       "depths [2,2,2,2], random-init weights, micro-batches of 64",
+                           "batch_per_gpu": B, "global_batch": B * world}, "models": res}
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    model = S.SwinWNet(error_matrix=two_channel, depths=DEPTHS)
+    sd = benchdata.make_state_dict(man[key], seed=1)
+    model.load_state_dict(sd, strict=True)
+    inf = S.SwinWNetInference(model, dev, max_batch=64)
+    call = (lambda x: inf(x)) if two_channel else (lambda x: inf(x, two_channel=False))
+
+    if cfg == 4:
+        sweep = []
+        for b in (1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096):
+            per_rank = max(1, b // world) if b >= world else (1 if rank < b else 0)
+            xb = make_inputs(max(per_rank, 1)).to(dev)
+            steps = max(2, min(args.steps, 2048 // max(per_rank, 1)))
+            for _ in range(2):
+                call(xb)
+            ms = timed(lambda: call(xb), steps)
+            inf._reset_outputs()
+            sweep.append({"global_batch": per_rank * world, "ms_per_step": ms / steps,
+                          "value": whole_job_rate(per_rank, world, steps, ms)})
+            del xb
+            torch.cuda.empty_cache()
+        best = max(sweep, key=lambda s: s["value"])
+        line = {"metric": METRIC, "value": best["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": 2,
+                "ms_per_step": best["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "bf16" if ops.operand_dtype() == torch.bfloat16 else "fp16", "data": "synthetic",
+                "config": {"workload": "configs[3]: multimodal ST pipeline, global batch sweep 1..4096 sharded over the ranks, "
+                                       "micro-batches of 64 per rank; value = best point", "global_batch": best["global_batch"]},
+                "sweep": sweep}
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    inf_fast = S.SwinWNetInference(model, dev, max_batch=64, cuda_graph=True) if args.graph else inf
+    x_host = make_inputs(B)
+    x_dev = x_host.to(dev)
+    cout = 2 if two_channel else 1
+    out_host = torch.empty(B, cout, 2 * H, 2 * W).pin_memory()
+
     def step_dev():
-        inf(x_dev)
+        call(x_dev)
 
     # one chunk per step: the H2D of step i+1 and the D2H of step i then overlap the compute of their neighbours across
-    # steps (copy streams), all inside the timed region; smaller chunks also overlap inside a step but run the deep,
-    # narrow layers of the net on half-filled waves
+    # steps (copy streams), all inside the timed region
     E2E_CHUNK = int(os.environ.get("SWN_E2E_CHUNK", B))
 
     def step_e2e():
         # public host-data call: pinned host inputs -> pinned host result, copies pipelined against compute in chunks
-        inf.run_host(x_host, out=out_host, chunk=E2E_CHUNK)
+        inf.run_host(x_host, out=out_host, chunk=E2E_CHUNK, two_channel=two_channel)
 
     for _ in range(W_):
         step_dev()
     sampler = ClockSampler(local)
     sampler.start()
-    ops.swin_block_fused, ops.mlp = hooks["fused"], hooks["mlp"]
+    ft = FamilyTimer(ops)
+    ft.install()
     n0 = ops.LAUNCH_COUNT
     ms = timed(step_dev, args.steps)
     launches = ops.LAUNCH_COUNT - n0
-    ops.swin_block_fused, ops.mlp = orig["fused"], orig["mlp"]
-    pk = peaks()
-    kern = {}
-    for name, label in (("fused", "swn::swin_fused_kernel + swin_attn_stream_kernel (fused LN1+qkv+W-MSA+proj[+LN2+MLP], C<=96)"),
-                        ("mlp", "swn::mlp_kernel + mlp_persist_kernel (fused LN2+fc1+GELU+fc2+residual, C>=96)")):
-        f = fam[name]
-        k_ms = sum(a.elapsed_time(b) for a, b in f["ev"]) / args.steps
-        tf = f["flop"] / args.steps / (k_ms / 1e3) / 1e12 if k_ms > 0 else 0.0
-        gbs = f["bytes"] / args.steps / (k_ms / 1e3) / 1e9 if k_ms > 0 else 0.0
-        kern[name] = {"kernel": label, "launches_per_step": len(f["ev"]) // max(args.steps, 1), "kernel_ms_per_step": k_ms,
-                      "kernel_share_of_step": k_ms / (ms / args.steps), "achieved_tflops": tf, "tensor_frac": tf / pk["tf_sust"],
-                      "achieved_gbs": gbs, "hbm_frac": gbs / pk["hbm"]}
-    dom = max(kern, key=lambda n: kern[n]["kernel_ms_per_step"])
-    # which roof bounds the family: its algorithmic intensity (FLOP per algorithmic byte) against the ridge of the two
-    # measured peaks.  The fused W-MSA / block family sits below the ridge (3C + 12.5 FLOP/B per token-block, C <= 96).
-    kd = kern[dom]
-    ridge = pk["tf_sust"] * 1e12 / (pk["hbm"] * 1e9)
-    intensity = fam[dom]["flop"] / max(fam[dom]["bytes"], 1.0)
-    hbm_bound = intensity < ridge
-    roof = {"bound": "hbm" if hbm_bound else "tensor", "kernel": kd["kernel"],
-            "achieved": kd["achieved_gbs"] if hbm_bound else kd["achieved_tflops"],
-            "peak": pk["hbm"] if hbm_bound else pk["tf_sust"], "unit": "GB/s" if hbm_bound else "TFLOP/s",
-            "frac": kd["hbm_frac"] if hbm_bound else kd["tensor_frac"], "traffic": TRAFFIC_NCU.get(dom),
-            "peak_source": pk["src"] + (" (copy bandwidth)" if hbm_bound else " (sustained bf16)"),
-            "intensity_flop_per_byte": intensity, "ridge_flop_per_byte": ridge,
-            "kernel_ms_per_step": kd["kernel_ms_per_step"], "kernel_share_of_step": kd["kernel_share_of_step"],
-            "tensor_tflops": kd["achieved_tflops"], "tensor_frac": kd["tensor_frac"],
-            "hbm_gbs": kd["achieved_gbs"], "hbm_frac": kd["hbm_frac"]}
+    ft.remove()
+    kern = ft.summary(args.steps, ms / args.steps, pk)
+    roof = roofline_of(kern, pk, traffic_table())
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
@@ -272,40 +494,49 @@ def main():
         graph_info = {"value": whole_job_rate(B, world, args.steps, ms_g), "unit": UNIT, "ms_per_step": ms_g / args.steps}
     value = whole_job_rate(B, world, args.steps, ms)
     e2e_v = whole_job_rate(B, world, args.steps, ms_e2e)
+    wl = ("SwinWNet multimodal ST pipeline [B,2,250,480] (configs[1])" if two_channel else
+          "SwinWNet diffraction-only ST pipeline [B,1,250,480], manual three-call pattern (configs[0])")
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W_,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if ops.operand_dtype() == torch.bfloat16 else "fp16", "data": "synthetic",
-            "config": {"workload": "SwinWNet multimodal ST pipeline [B,2,250,480] (configs[1]), depths [2,2,2,2], "
-                                   "random-init weights", "batch_per_gpu": B, "global_batch": B * world,
+            "config": {"workload": wl + ", depths [2,2,2,2], random-init weights", "batch_per_gpu": B, "global_batch": B * world,
                        "l2_policy": "per-step working set (>2 GB of activations) exceeds the 126 MB L2"},
             "model_tflops": GFLOP_PER_DIFFRACTION * value / 1e3,
+            "model_tensor_frac": GFLOP_PER_DIFFRACTION * value / 1e3 / world / pk["tf_sust"],
             "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4,
                     "d2h_bytes_per_step": out_host.numel() * 4},
             "gpu_launches": launches,
             "roofline": roof,
             "kernels": kern,
+            "kernel_share_sum": sum(k["kernel_share_of_step"] for k in kern.values()),
             "clocks": sampler.summary()}
     if graph_info:
         line["graph"] = graph_info
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count()
-        torch.set_num_threads(cores)
-        from oracle import swinwnet_oracle as O    # the checker, executed only for the reported CPU baseline
-        sd = benchdata.make_state_dict(man["wnet_em"], seed=1)
-        xs = x_host[:1].clone()
-        with torch.no_grad():
-            O.st_pipeline(sd, xs)
-            t0 = time.perf_counter()
-            n = 4
-            for _ in range(n):
-                O.st_pipeline(sd, xs)
-            dt = (time.perf_counter() - t0) / n
-        line["cpu_baseline"] = {"value": 1.0 / dt, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"{n} x 1 diffraction of the same workload, fp32 torch CPU oracle"}
+    rc = 0
+    if not args.no_parity_check:
+        # correctness of the configuration that was just timed (every rank checks its own shard)
+        pc = parity_check(inf, x_dev, sd, two_channel)
+        ok = torch.tensor([1.0 if pc["ok"] else 0.0], device=dev)
+        if dist is not None:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        pc["ok_all_ranks"] = bool(ok.item() > 0.5)
+        line["parity_check"] = pc
+        rc = 0 if pc["ok_all_ranks"] else 3
+    if rank == 0 and world == 1:
+        if not args.no_library_bar:
+            inf._reset_outputs()
+            torch.cuda.empty_cache()
+            line["library_bar"] = library_bar(dev)
+        if not args.no_cpu_baseline:
+            _, _, cb = cpu_reference_rate(4, 1)
+            line["cpu_baseline"] = cb
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+    if rc:
+        sys.stderr.write("bench.py: parity_check FAILED\n")
+        sys.exit(rc)
 
 
 if __name__ == "__main__":

@@ -116,7 +116,7 @@ def window_attention(sd: SD, prefix: str, xn: Tensor, res: Tuple[int, int], num_
     if shift > 0:
         g = torch.roll(g, shifts=(-shift, -shift), dims=(1, 2))
     Hp, Wp = -(-H // ws) * ws, -(-W // ws) * ws
-    gp = torch.zeros(B, Hp, Wp, C, dtype=xn.dtype)
+    gp = torch.zeros(B, Hp, Wp, C, dtype=xn.dtype, device=xn.device)
     gp[:, :H, :W] = g                      # zero pad AFTER the norm (SwinWNet.py:242,254)
     nWy, nWx = Hp // ws, Wp // ws
     win = gp.view(B, nWy, ws, nWx, ws, C).permute(0, 1, 3, 2, 4, 5).reshape(B * nWy * nWx, ws * ws, C)
@@ -127,12 +127,12 @@ def window_attention(sd: SD, prefix: str, xn: Tensor, res: Tuple[int, int], num_
     v = qkv[:, :, 2].permute(0, 2, 1, 3)
     att = q @ k.transpose(-1, -2)                                   # [Bw,nH,25,25]
     table = sd[prefix + "relative_position_bias_table"]            # [81,nH]
-    bias = table[rel_pos_index(ws).reshape(-1)].view(ws * ws, ws * ws, num_heads).permute(2, 0, 1)
+    bias = table[rel_pos_index(ws).reshape(-1).to(table.device)].view(ws * ws, ws * ws, num_heads).permute(2, 0, 1)
     att = att + bias.unsqueeze(0)
     if shift > 0:
-        rid = shift_region_ids(Hp, Wp, ws, shift)
+        rid = shift_region_ids(Hp, Wp, ws, shift).to(xn.device)
         rw = rid.view(nWy, ws, nWx, ws).permute(0, 2, 1, 3).reshape(nWy * nWx, ws * ws)
-        m = torch.where(rw[:, :, None] == rw[:, None, :], 0.0, -100.0)       # [nW,25,25]
+        m = torch.where(rw[:, :, None] == rw[:, None, :], 0.0, -100.0).to(xn.dtype)       # [nW,25,25]
         att = (att.view(B, nWy * nWx, num_heads, ws * ws, ws * ws) + m[None, :, None]).view(-1, num_heads, ws * ws, ws * ws)
     att = torch.softmax(att, dim=-1)
     o = (att @ v).permute(0, 2, 1, 3).reshape(-1, ws * ws, C)
@@ -168,7 +168,7 @@ def patch_merging(sd: SD, prefix: str, x: Tensor, res):
     H, W = res
     assert L == H * W, "input feature has wrong size"
     He, We = H + (H & 1), W + (W & 1)
-    g = torch.zeros(B, He, We, C, dtype=x.dtype)
+    g = torch.zeros(B, He, We, C, dtype=x.dtype, device=x.device)
     g[:, :H, :W] = x.view(B, H, W, C)     # zero pad BEFORE the norm (SwinWNet.py:295-312)
     cat = torch.cat([g[:, 0::2, 0::2], g[:, 1::2, 0::2], g[:, 0::2, 1::2], g[:, 1::2, 1::2]], -1)
     cat = cat.reshape(B, -1, 4 * C)
@@ -181,7 +181,7 @@ def patch_expanding(sd: SD, prefix: str, x: Tensor, res):
     H, W = res
     assert L == H * W, "input feature has wrong size"
     e = linear(x, sd[prefix + "expand.weight"]).view(B, H, W, 2, 2, C // 2)
-    out = torch.empty(B, 2 * H, 2 * W, C // 2, dtype=x.dtype)
+    out = torch.empty(B, 2 * H, 2 * W, C // 2, dtype=x.dtype, device=x.device)
     for i in range(2):
         for j in range(2):
             out[:, i::2, j::2] = e[:, :, :, i, j]      # pixel (2h+i,2w+j) <- channel group 2i+j
@@ -236,7 +236,7 @@ def decoder(sd: SD, prefix: str, x: Tensor, res, skips: List[Tensor], rlist, dep
 def conv3x3_nhwc(x: Tensor, w: Tensor, b: Tensor) -> Tensor:
     """x [B,H,W,Ci], w [Co,Ci,3,3], zero padding 1 -> [B,H,W,Co]."""
     B, H, W, Ci = x.shape
-    xp = torch.zeros(B, H + 2, W + 2, Ci, dtype=x.dtype)
+    xp = torch.zeros(B, H + 2, W + 2, Ci, dtype=x.dtype, device=x.device)
     xp[:, 1:-1, 1:-1] = x
     acc = b.view(1, 1, 1, -1).expand(B, H, W, -1).clone()
     for dy in range(3):
@@ -250,7 +250,7 @@ def bilinear_up(x: Tensor, s: int) -> Tensor:
     B, h, w = x.shape
 
     def taps(n):
-        d = torch.arange(n * s, dtype=torch.float32)
+        d = torch.arange(n * s, dtype=torch.float32, device=x.device)
         src = torch.clamp((d + 0.5) / s - 0.5, min=0.0)
         i0 = src.floor().long().clamp(max=n - 1)
         i1 = (i0 + 1).clamp(max=n - 1)
