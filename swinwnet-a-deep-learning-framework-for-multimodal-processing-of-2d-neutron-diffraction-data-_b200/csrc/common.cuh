@@ -167,6 +167,15 @@ __device__ __forceinline__ void fence_barrier_init() {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// One arrival per WARP (the barrier is initialised with the number of warps, not threads): every lane has issued its own
+// fences (fence.proxy.async / tcgen05.fence::before_thread_sync) for its own writes, __syncwarp orders them before lane
+// 0's releasing arrive.  Measured reason (profiles/r2a_mlp_role_waits.txt): with 256 per-thread arrivals on two barriers
+// per hidden chunk the epilogue warps of the MLP kernels spent ~1.6 k cycles per chunk on ~340 useful instructions —
+// mbarrier arrivals on one address serialise.
+__device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");

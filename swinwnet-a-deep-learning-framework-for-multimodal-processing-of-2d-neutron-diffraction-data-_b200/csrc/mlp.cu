@@ -89,11 +89,11 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(const MlpParams p) 
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&sh->hacc_full[b], 1);
-      mbar_init(&sh->hacc_empty[b], MLP_EPI_THREADS);
-      mbar_init(&sh->hs_full[b], MLP_EPI_THREADS);
+      mbar_init(&sh->hacc_empty[b], MLP_EPI_THREADS / 32);
+      mbar_init(&sh->hs_full[b], MLP_EPI_THREADS / 32);
       mbar_init(&sh->hs_empty[b], 1);
     }
-    mbar_init(&sh->a_ready, MLP_THREADS);
+    mbar_init(&sh->a_ready, MLP_WARPS);
     mbar_init(&sh->y_full, 1);
     fence_barrier_init();
   }
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(const MlpParams p) 
     });
   }
   fence_proxy_async();
-  mbar_arrive(&sh->a_ready);
+  mbar_arrive_warp(&sh->a_ready);
   if (warp == 1) MLP_PROF_ADD(12, t_cta0);
 
   if (warp == 0) {
@@ -276,8 +276,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(const MlpParams p) 
       }
       tc_fence_before();
       fence_proxy_async();
-      mbar_arrive(&sh->hacc_empty[abuf]);
-      mbar_arrive(&sh->hs_full[buf]);
+      mbar_arrive_warp(&sh->hacc_empty[abuf]);
+      mbar_arrive_warp(&sh->hs_full[buf]);
       if (warp == 2) MLP_PROF_ADD(8, t_g0);
     }
     // residual rows in the transposed ownership (common.cuh), fetched one column block ahead: the first block is

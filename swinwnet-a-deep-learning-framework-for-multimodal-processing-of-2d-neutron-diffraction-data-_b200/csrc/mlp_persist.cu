@@ -94,16 +94,16 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&sh->in_full[b], 1);
-      mbar_init(&sh->in_empty[b], MP_EPI_THREADS);
+      mbar_init(&sh->in_empty[b], MP_EPI_THREADS / 32);
       mbar_init(&sh->hacc_full[b], 1);
-      mbar_init(&sh->hacc_empty[b], MP_EPI_THREADS);
-      mbar_init(&sh->hs_full[b], MP_EPI_THREADS);
+      mbar_init(&sh->hacc_empty[b], MP_EPI_THREADS / 32);
+      mbar_init(&sh->hs_full[b], MP_EPI_THREADS / 32);
       mbar_init(&sh->hs_empty[b], 1);
     }
-    mbar_init(&sh->a_full, MP_LN_WARPS * 32);
+    mbar_init(&sh->a_full, MP_LN_WARPS);
     mbar_init(&sh->a_empty, 1);
     mbar_init(&sh->y_full, 1);
-    mbar_init(&sh->y_empty, MP_EPI_THREADS);
+    mbar_init(&sh->y_empty, MP_EPI_THREADS / 32);
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < 4 * C; i += MP_THREADS) b1s[i] = p.b1[i];
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
           return __ldg(reinterpret_cast<const float4*>(xg + mr * C + k));
         });
         fence_proxy_async();
-        mbar_arrive(&sh->a_full);
+        mbar_arrive_warp(&sh->a_full);
         continue;
       }
       if (warp == 4) { MP_TIMED(12, mbar_wait(&sh->in_full[s], ((uint32_t)it >> 1) & 1u)); MP_TIMED(13, mbar_wait(&sh->a_empty, ((uint32_t)it & 1u) ^ 1u)); }
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
         *reinterpret_cast<uint4*>(a_smem + (k >> 6) * A_KBLOCK_BYTES + sw128_offset(row, k & 63)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
       fence_proxy_async();
-      mbar_arrive(&sh->a_full);
+      mbar_arrive_warp(&sh->a_full);
 #if SWN_MLP_PROFILE
       if (p.phase_cycles && warp == 4 && lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.phase_cycles + 14), (unsigned long long)(clock64() - t_ln0));
 #endif
@@ -355,8 +355,8 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
         }
         tc_fence_before();
         fence_proxy_async();
-        mbar_arrive(&sh->hacc_empty[buf]);
-        mbar_arrive(&sh->hs_full[buf]);
+        mbar_arrive_warp(&sh->hacc_empty[buf]);
+        mbar_arrive_warp(&sh->hs_full[buf]);
 #if SWN_MLP_PROFILE
         if (p.phase_cycles && warp == 8 && lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.phase_cycles + 8), (unsigned long long)(clock64() - t_g0));
 #endif
@@ -432,8 +432,8 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
       if (p.phase_cycles && warp == 8 && lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.phase_cycles + 10), (unsigned long long)(clock64() - t_f0));
 #endif
       tc_fence_before();
-      mbar_arrive(&sh->y_empty);
-      if (!DIRECT) mbar_arrive(&sh->in_empty[s]);
+      mbar_arrive_warp(&sh->y_empty);
+      if (!DIRECT) mbar_arrive_warp(&sh->in_empty[s]);
     }
   }
   tc_fence_before();

@@ -60,9 +60,9 @@ __global__ void __launch_bounds__(RG_THREADS, 1) rowgemm_kernel(const RowGemmPar
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&sh->tmem_full[b], 1);
-      mbar_init(&sh->tmem_empty[b], epi_count);
+      mbar_init(&sh->tmem_empty[b], epi_count / 32);
     }
-    mbar_init(&sh->a_ready, RG_THREADS);
+    mbar_init(&sh->a_ready, RG_THREADS / 32);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(&sh->tmem_base, tmem_cols);
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) rowgemm_kernel(const RowGemmPar
     }
   }
   fence_proxy_async();
-  mbar_arrive(&sh->a_ready);
+  mbar_arrive_warp(&sh->a_ready);
 
   if (warp == 0) {
     // ===== weight producer: remaining tiles, consumption order =====
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) rowgemm_kernel(const RowGemmPar
           }
         }
         tc_fence_before();
-        mbar_arrive(&sh->tmem_empty[half]);
+        mbar_arrive_warp(&sh->tmem_empty[half]);
       }
     } else {
       const bool vec8 = (p.ldo % 8 == 0) && (p.n_valid % 8 == 0);
@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) rowgemm_kernel(const RowGemmPar
           }
         }
         tc_fence_before();
-        mbar_arrive(&sh->tmem_empty[buf]);
+        mbar_arrive_warp(&sh->tmem_empty[buf]);
       }
     }
   }

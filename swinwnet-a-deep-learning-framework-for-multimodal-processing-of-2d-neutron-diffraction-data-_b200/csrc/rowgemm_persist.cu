@@ -61,13 +61,13 @@ __global__ void __launch_bounds__(RP_THREADS, 1) rowgemm_persist_kernel(const Ro
     mbar_init(&sh->w_full, 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(&sh->in_full[b], 1);
-      mbar_init(&sh->in_empty[b], RP_EPI_THREADS);
+      mbar_init(&sh->in_empty[b], RP_EPI_THREADS / 32);
     }
-    mbar_init(&sh->a_full, RP_CVT_WARPS * 32);
+    mbar_init(&sh->a_full, RP_CVT_WARPS);
     mbar_init(&sh->a_empty, 1);
     for (int b = 0; b < RP_MAX_ACC; ++b) {
       mbar_init(&sh->acc_full[b], 1);
-      mbar_init(&sh->acc_empty[b], RP_EPI_THREADS);
+      mbar_init(&sh->acc_empty[b], RP_EPI_THREADS / 32);
     }
     fence_barrier_init();
   }
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(RP_THREADS, 1) rowgemm_persist_kernel(const Ro
         *reinterpret_cast<uint4*>(a_smem + (k >> 6) * A_KBLOCK_BYTES + sw128_offset(row, k & 63)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
       fence_proxy_async();
-      mbar_arrive(&sh->a_full);
+      mbar_arrive_warp(&sh->a_full);
     }
   } else if (warp >= 8) {
     // ===== epilogue warps 8..15: two warps per TMEM lane group, interleaved 16-column blocks =====
@@ -281,13 +281,13 @@ __global__ void __launch_bounds__(RP_THREADS, 1) rowgemm_persist_kernel(const Ro
           }
         }
         tc_fence_before();
-        mbar_arrive(&sh->acc_empty[buf]);
+        mbar_arrive_warp(&sh->acc_empty[buf]);
         if (++buf == nacc) {
           buf = 0;
           acc_ph ^= 1u;
         }
       }
-      mbar_arrive(&sh->in_empty[s]);   // staging (residual rows) of this tile no longer needed
+      mbar_arrive_warp(&sh->in_empty[s]);   // staging (residual rows) of this tile no longer needed
     }
   }
   tc_fence_before();

@@ -19,12 +19,15 @@ lowered onto the C ABI in ``ops.py``:
                             + swn_rowgemm (out_proj, q + gamma*o epilogue)             SwinWNet.py:778-783
     patch embed / heads  -> swn_patch_embed / swn_seg_head / swn_recon_head            SwinWNet.py:53-82,507-531,682-688
 
-Only inference (``torch.no_grad()``) is implemented; a forward with autograd enabled raises.
+With autograd enabled (the reference trainers: Segmentator_pretrain.py:185, FullModel_supervised_trainer.py:231-288) every
+leaf operator goes through ``autograd.KernelOp``: the forward is the same kernel lowering, the backward re-evaluates
+the operator with its fp32 torch restatement (``torch_ref.py``) on the saved inputs.  Under ``torch.no_grad()`` nothing of
+that is touched (in-place ping-pong buffers, no saved tensors).
 """
 import torch
 import torch.nn as nn
 
-from . import ops, packing
+from . import autograd, ops, packing, torch_ref
 
 WINDOW = 5
 FUSED_BLOCK = True   # route shift-0 blocks of the widths below through the single-kernel paths (csrc/swin_fused.cu)
@@ -35,8 +38,12 @@ FUSED_ATTN = {(96, 3), (96, 6)}                       # instances of swin_attn_s
 def _check_infer(x):
     if not x.is_cuda:
         raise RuntimeError("swinwnet_b200: forward needs CUDA tensors (B200); there is no CPU fallback")
-    if torch.is_grad_enabled():
-        raise RuntimeError("swinwnet_b200: only inference is implemented — call under torch.no_grad()")
+
+
+def _grad():
+    """autograd path?  (torch.autograd.Function.forward runs with grad mode off, so the kernel lowering below is what
+    KernelOp.forward executes)"""
+    return torch.is_grad_enabled()
 
 
 class _PackCache:
@@ -69,6 +76,14 @@ class ScaleAwarePatchEmbed(nn.Module):
 
     def forward(self, x, scale_factor=1):
         _check_infer(x)
+        if _grad():
+            ps, s = self.patch_size, scale_factor
+            H, W = x.shape[-2:]
+            padded = (H + (ps * s - H % ps * s) % ps * s, W + (ps * s - W % ps * s) % ps * s)
+            out = autograd.op(lambda x_, *p: self.forward(x_, scale_factor)[0],
+                              lambda x_, *p: torch_ref.patch_embed(x_, *p, scale=scale_factor, patch=ps),
+                              x, self.proj.weight, self.proj.bias, self.norm.weight, self.norm.bias)
+            return out, padded
         if self.patch_size != 2 or self.proj.out_channels != 48:
             raise RuntimeError("swinwnet_b200: kernels are built for patch_size=2, embed_dim=48")
         B, C, H, W = x.shape
@@ -213,8 +228,21 @@ class SwinTransformerBlock(nn.Module):
         ops.mlp(tmp, out, M, C, pk["n2w"], pk["n2b"], Wm, pk["b1"], b2p, self.norm2.eps)
         return out
 
+    def _params(self):
+        a = self.attn
+        return (self.norm1.weight, self.norm1.bias, a.qkv.weight, a.qkv.bias, a.relative_position_bias_table, a.proj.weight,
+                a.proj.bias, self.norm2.weight, self.norm2.bias, self.mlp[0].weight, self.mlp[0].bias, self.mlp[3].weight,
+                self.mlp[3].bias)
+
     def forward(self, x, resolution):
         _check_infer(x)
+        if _grad():
+            if self.shift_size:
+                raise NotImplementedError("swinwnet_b200: shift_size > 0 has no backward (the reference cannot run it either, "
+                                          "SwinWNet.py:147)")
+            res, nh = tuple(resolution), self.num_heads
+            return autograd.op(lambda x_, *p: self.forward(x_, res), lambda x_, *p: torch_ref.swin_block(x_, res, nh, *p),
+                               x, *self._params())
         x = x.float().contiguous()
         return self.run(x, resolution, torch.empty_like(x))
 
@@ -230,6 +258,10 @@ class BasicLayer(nn.Module):
 
     def run(self, x, resolution, inplace=False):
         """returns the layer output; with inplace=True the caller gives up x (it may be overwritten or returned)."""
+        if _grad():                       # autograd path: no buffer reuse, one KernelOp per block
+            for blk in self.blocks:
+                x = blk(x, resolution)
+            return x
         if FUSED_BLOCK and all((b.dim, b.num_heads) in FUSED_WHOLE and b.shift_size == 0 for b in self.blocks):
             # single-kernel blocks never run in place: ping-pong between two buffers
             spare = None
@@ -247,7 +279,7 @@ class BasicLayer(nn.Module):
 
     def forward(self, x, resolution):
         _check_infer(x)
-        return self.run(x.float().contiguous(), resolution)
+        return self.run(x if _grad() else x.float().contiguous(), resolution)
 
 
 class PatchMerging(nn.Module):
@@ -264,6 +296,11 @@ class PatchMerging(nn.Module):
         H, W = resolution
         assert L == H * W, "input feature has wrong size"
         Ho, Wo = (H + 1) // 2, (W + 1) // 2
+        if _grad():
+            res = (H, W)
+            out = autograd.op(lambda x_, *p: self.forward(x_, res)[0], lambda x_, *p: torch_ref.patch_merging(x_, res, *p),
+                              x, self.reduction.weight, self.norm.weight, self.norm.bias)
+            return out, (Ho, Wo)
 
         def build():
             nv = packing.choose_chunk(2 * C, 64 if 4 * C > 384 else 256)   # K=768: the A tile alone is 192 KB
@@ -292,6 +329,13 @@ class PatchExpanding(nn.Module):
         Hs, Ws = target_res if target_res is not None else (2 * H, 2 * W)
         assert 2 * H >= Hs and 2 * W >= Ws
         Cg = C // 2
+        if _grad():
+            assert out is None, "the autograd path allocates its own outputs"
+            res, tgt = (H, W), (Hs, Ws)
+            y = autograd.op(lambda x_, *p: self.run(x_.float().contiguous(), res, tgt)[0],
+                            lambda x_, *p: torch_ref.patch_expanding(x_, res, tgt, *p),
+                            x, self.expand.weight, self.norm.weight, self.norm.bias)
+            return y, (Hs, Ws)
 
         def build():
             return packing.pack_rowgemm(self.expand.weight, None, Cg) + (_f32(self.norm.weight), _f32(self.norm.bias))
@@ -305,7 +349,7 @@ class PatchExpanding(nn.Module):
 
     def forward(self, x, resolution):
         _check_infer(x)
-        return self.run(x.float().contiguous(), resolution)
+        return self.run(x if _grad() else x.float().contiguous(), resolution)
 
 
 class SwinEncoder(nn.Module):
@@ -363,6 +407,16 @@ class SwinDecoder(nn.Module):
     def forward(self, x, resolution, skips, skip_res_list):
         _check_infer(x)
         skips, skip_res_list = skips[-2::-1], skip_res_list[-2::-1]
+        if _grad():
+            for i in range(len(self.swin_blocks)):
+                Hs, Ws = skip_res_list[i]
+                xe, _ = self.ups[i].run(x, resolution, (Hs, Ws))                 # expand + crop_to_res
+                cat = self.swin_blocks[i].run(torch.cat([xe, skips[i].float()], dim=-1), (Hs, Ws))
+                lin = self.linears[i]
+                x = autograd.op(lambda c_, *p, i=i: self._linear_infer(i, c_), lambda c_, w, b: torch_ref.linear(c_, w, b),
+                                cat, lin.weight, lin.bias)
+                resolution = (Hs, Ws)
+            return x, resolution
         for i in range(len(self.swin_blocks)):
             B, L, C = x.shape                       # C = concat width of this stage
             Hs, Ws = skip_res_list[i]
@@ -373,17 +427,25 @@ class SwinDecoder(nn.Module):
             assert skip.shape == (B, Hs * Ws, half)
             ops.copy_cols(skip, half, cat, half, C, B * Hs * Ws, half)       # skip -> channels [C/2, C)
             cat = self.swin_blocks[i].run(cat, (Hs, Ws), inplace=True)
-            lin = self.linears[i]
-
-            def build():
-                nv = packing.choose_chunk(half, 256)
-                return packing.pack_rowgemm(lin.weight, lin.bias, nv) + (nv,)
-            Wp, bp, NT, nch, nv = self._caches[i].get([lin.weight, lin.bias], build)
-            x = torch.empty(B, Hs * Ws, half, device=cat.device, dtype=torch.float32)
-            ops.rowgemm(A=cat, a_mode=ops.A_F32, M=B * Hs * Ws, K=C, lda=C, Wp=Wp, NT=NT, nchunks=nch, n_valid=nv,
-                        e_mode=ops.E_F32, bias=bp, out=x, ldo=half)
+            x = self._linear_infer(i, cat)
             resolution = (Hs, Ws)
         return x, resolution
+
+    def _linear_infer(self, i, cat):
+        """decoder stage linear 2c -> c on the raw fp32 stream (SwinWNet.py:489)"""
+        lin = self.linears[i]
+        cat = cat.float().contiguous()
+        B, L, C = cat.shape
+        half = C // 2
+
+        def build():
+            nv = packing.choose_chunk(half, 256)
+            return packing.pack_rowgemm(lin.weight, lin.bias, nv) + (nv,)
+        Wp, bp, NT, nch, nv = self._caches[i].get([lin.weight, lin.bias], build)
+        x = torch.empty(B, L, half, device=cat.device, dtype=torch.float32)
+        ops.rowgemm(A=cat, a_mode=ops.A_F32, M=B * L, K=C, lda=C, Wp=Wp, NT=NT, nchunks=nch, n_valid=nv,
+                    e_mode=ops.E_F32, bias=bp, out=x, ldo=half)
+        return x
 
 
 class SegmentationHead(nn.Module):
@@ -400,6 +462,11 @@ class SegmentationHead(nn.Module):
         up = self.patch_size * scale_factor
         Hq, Wq = H // up, W // up
         assert N == Hq * Wq and C == 48
+        if _grad():
+            res, c1, c2 = (H, W), self.seg_head[0], self.seg_head[2]
+            return autograd.op(lambda x_, *p: self.forward(x_.float().contiguous(), res, scale_factor),
+                               lambda x_, *p: torch_ref.segmentation_head(x_, res, scale_factor, *p, patch=self.patch_size),
+                               x, c1.weight, c1.bias, c2.weight, c2.bias)
         lowres = torch.empty(B, Hq, Wq, device=x.device, dtype=torch.float32)
         Hout, Wout = min(H, Hq * up), min(W, Wq * up)
         out = torch.empty(B, 1, Hout, Wout, device=x.device, dtype=torch.float32)
@@ -429,10 +496,18 @@ class UpscalingHead(nn.Module):
         for i in range(2):
             x, res = self.ups[i].run(x, res)
             x = self.swin_blocks[i].run(x, res, inplace=True)
+        return self._tail(x, res, crop)
+
+    def _tail(self, x, res, crop):
+        B = x.shape[0]
         Hh, Wh = res
         c1, c2 = self.reconstruction[0], self.reconstruction[2]
         Cout = c2.out_channels
         Hout, Wout = (min(crop[0], Hh), min(crop[1], Wh)) if crop is not None else (Hh, Wh)
+        if _grad():
+            r, cr = tuple(res), (Hout, Wout)
+            return autograd.op(lambda x_, *p: self._tail(x_.float().contiguous(), r, cr),
+                               lambda x_, *p: torch_ref.recon_tail(x_, r, cr, *p), x, c1.weight, c1.bias, c2.weight, c2.bias)
         out = torch.empty(B, Cout, Hout, Wout, device=x.device, dtype=torch.float32)
         ops.recon_head(x, _f32(c1.weight), _f32(c1.bias), _f32(c2.weight), _f32(c2.bias), out, B, Hh, Wh, Cout, Hout, Wout)
         return out
@@ -452,6 +527,12 @@ class CrossAttentionBlock(nn.Module):
         B, Lq, C = q.shape
         Lk = kv.shape[1]
         a = self.attn
+        if _grad():
+            nh = a.num_heads
+            return autograd.op(lambda q_, kv_, *p: self.forward(q_, kv_),
+                               lambda q_, kv_, *p: torch_ref.cross_attention_block(q_, kv_, nh, *p),
+                               q, kv, a.in_proj_weight, a.in_proj_bias, a.out_proj.weight, a.out_proj.bias, self.norm_q.weight,
+                               self.norm_q.bias, self.norm_kv.weight, self.norm_kv.bias, self.gamma)
 
         def build():
             Wi, bi = a.in_proj_weight, a.in_proj_bias
