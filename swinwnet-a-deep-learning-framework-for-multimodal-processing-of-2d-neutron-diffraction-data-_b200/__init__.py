@@ -4,6 +4,6 @@ modules and the ``SwinWNetInference`` pipeline, lowered onto hand-written CUDA k
 repo-root ``swinwnet_b200.py`` loader; the directory name itself is not a valid Python identifier)."""
 from .model import SwinWNet, SwinUNet, SwinUNetSR  # noqa: F401
 from .pipeline import SwinWNetInference  # noqa: F401
-from . import ops, packing, _lib, checkpoint, physics, dist  # noqa: F401
+from . import ops, packing, _lib, checkpoint, physics, dist, train, autograd, torch_ref  # noqa: F401
 
 __all__ = ["SwinWNet", "SwinUNet", "SwinUNetSR", "SwinWNetInference", "ops", "packing", "checkpoint", "physics"]

@@ -79,7 +79,7 @@ def load():
         # the digest of the sources + flags is compiled into the library: a stale build must not run against newer
         # packing / Python code (the weight images and parameter structs are defined on both sides)
         from . import build as _build
-        if os.path.isdir(_build.CSRC) and not os.environ.get("SWN_SKIP_DIGEST_CHECK"):
+        if os.path.isdir(_build.CSRC) and not VARIANT.startswith("x"):   # x*: scratch A/B builds (tools/), flags vary
             want, have = _build.digest(VARIANT), lib.swn_build_digest().decode()
             if want != have:
                 raise RuntimeError(f"{LIB_PATH} is stale (built from other sources/flags: {have[:12]} != {want[:12]}); "

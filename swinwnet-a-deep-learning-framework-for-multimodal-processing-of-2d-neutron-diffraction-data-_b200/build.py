@@ -20,7 +20,10 @@ SOURCES = ["api.cu", "rowgemm.cu", "rowgemm_persist.cu", "mlp.cu", "mlp_persist.
 HEADERS = ["common.cuh", "kernels.h", os.path.join("..", "..", "include", "swinwnet_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
-VARIANTS = {"": [], "bf16": ["-DSWN_OPERAND_BF16=1"], "prof": ["-DSWN_MLP_PROFILE=1", "-DSWN_TUNING_HOOKS=1"]}
+VARIANTS = {"": [], "bf16": ["-DSWN_OPERAND_BF16=1"], "prof": ["-DSWN_MLP_PROFILE=1", "-DSWN_TUNING_HOOKS=1"],
+            # scratch variants for A/B experiments on the GPU box (tools/gpu_call_ab.sh); flags come from SWN_X<n>_FLAGS at BUILD time
+            "x1": os.environ.get("SWN_X1_FLAGS", "-DSWN_EXP=1").split(), "x2": os.environ.get("SWN_X2_FLAGS", "-DSWN_EXP=2").split(),
+            "x3": os.environ.get("SWN_X3_FLAGS", "-DSWN_EXP=3").split()}
 
 
 def lib_path(variant=""):

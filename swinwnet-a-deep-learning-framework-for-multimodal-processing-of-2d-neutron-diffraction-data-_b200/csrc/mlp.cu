@@ -42,9 +42,16 @@ namespace swn {
 #define MLP_TIMED(slot, stmt) do { stmt; } while (0)
 #endif
 
-constexpr int MLP_WARPS = 10;
+// epilogue warps per TMEM lane group (they split the 16-column blocks of a hidden chunk / of Y).  The GELU epilogue is
+// bound by MUFU.TANH (8 issue cycles per warp-element per SM sub-partition, tools/micro/pipes.cu) and by dependent-issue
+// latency: with 2 warps per sub-partition it ran at ~15 cycles per warp-element, with 4 it approaches the MUFU rate.
+#ifndef SWN_MLP_EPI_SPLIT
+#define SWN_MLP_EPI_SPLIT 4
+#endif
+constexpr int MLP_EPI_SPLIT = SWN_MLP_EPI_SPLIT;
+constexpr int MLP_WARPS = 2 + 4 * MLP_EPI_SPLIT;
 constexpr int MLP_THREADS = MLP_WARPS * 32;
-constexpr int MLP_EPI_THREADS = 256;
+constexpr int MLP_EPI_THREADS = 128 * MLP_EPI_SPLIT;
 
 struct MlpSmem {
   uint64_t full[8];
@@ -227,14 +234,14 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(const MlpParams p) 
     }
     MLP_PROF_ADD(5, t_mma0);
   } else {
-    // ===== epilogue warps 2..9: thread <-> row; the two warps of a lane group split the columns =====
+    // ===== epilogue warps 2..: thread <-> row; the MLP_EPI_SPLIT warps of a lane group split the columns =====
     const int lg = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = (warp - 2) >> 2;      // column part of this warp, 0 .. MLP_EPI_SPLIT-1
     const int r = lg * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
     // 16-column blocks of the hidden chunk owned by this warp
-    const int cb_beg = (steps2 & 1) ? (half ? steps2 : 0) : half * (steps2 >> 1);
-    const int cb_end = (steps2 & 1) ? steps2 : cb_beg + (steps2 >> 1);
+    const int cb_beg = half * steps2 / MLP_EPI_SPLIT;
+    const int cb_end = (half + 1) * steps2 / MLP_EPI_SPLIT;
     float v[32];
     for (int j = 0; j < nj; ++j) {
       const int buf = j & 1;                       // hidden smem tile
@@ -297,8 +304,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(const MlpParams p) 
     tc_fence_after();
     // the hidden tiles are free by now and serve as the per-warp 2 KB transposition scratch
     uint8_t* scr = hs_smem + (warp - 2) * EPI_SCRATCH_BYTES;
-    for (int cb = half; cb < (C16 >> 4); cb += 2) {
-      load_res(cb + 2, xr_nxt);
+    for (int cb = half; cb < (C16 >> 4); cb += MLP_EPI_SPLIT) {
+      load_res(cb + MLP_EPI_SPLIT, xr_nxt);
       tmem_ld16(lane_addr + (uint32_t)(cb * 16), v);
       tmem_ld_wait();
 #pragma unroll

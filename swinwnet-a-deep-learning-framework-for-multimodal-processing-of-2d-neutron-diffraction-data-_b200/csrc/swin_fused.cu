@@ -20,6 +20,10 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#ifndef SWN_FUSED_SPIN
+#define SWN_FUSED_SPIN 0
+#endif
+
 namespace swn {
 
 namespace {
@@ -312,7 +316,11 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
   // every barrier is waited for exactly once by every thread, so the bits stay in step with the barriers
   uint32_t phases = 0;
   auto wait_bar = [&](uint64_t* bar, int bit) {   // warp 0 polls the mbarrier, the CTA barrier releases everybody else
+#if SWN_FUSED_SPIN
+    if (warp == 0) mbar_wait_spin(bar, (phases >> bit) & 1u);
+#else
     if (warp == 0) mbar_wait(bar, (phases >> bit) & 1u);
+#endif
     phases ^= 1u << bit;
   };
   constexpr float inv_c = 1.0f / (float)C;

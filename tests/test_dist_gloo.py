@@ -94,3 +94,46 @@ def test_grad_reducer_buckets_average_and_tolerate_missing_grads():
         b = loc1[name] if loc1[name] is not None else torch.zeros_like(red0[name])
         assert torch.allclose(red0[name], (a + b) / 2, atol=1e-7) and torch.equal(red0[name], red1[name])
     assert loc1["dec.weight"] is None and red1["dec.weight"] is not None
+
+
+def _sync_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import swinwnet_b200 as S
+    torch.manual_seed(0)
+    model = torch.nn.ModuleDict({"enc": torch.nn.Linear(6, 5), "dec": torch.nn.Linear(5, 3), "ca": torch.nn.Linear(5, 5)})
+    sync = S.train.DistributedGradSync(model)             # hooks: every backward ends with the all-reduce
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-2)
+    g = torch.Generator().manual_seed(100 + rank)
+    hist = []
+    for step in range(4):                                  # even steps skip "ca" (grad None everywhere), odd steps use it
+        x = torch.randn(7, 6, generator=g)
+        h = model["enc"](x)
+        if step % 2:
+            h = h + model["ca"](h)
+        loss = (model["dec"](h) ** 2).mean()
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        hist.append((sync.reduced_elements, model["ca"].weight.grad is None))
+        opt.step()
+    out.put((rank, hist, {n: p.detach().flatten().tolist() for n, p in model.named_parameters()}))
+    dist.destroy_process_group()
+
+
+def test_distributed_grad_sync_hooks_keep_replicas_identical():
+    """the even / odd unused-parameter pattern of FullModel_supervised_trainer.py:231-288 through the backward-end hook:
+    parameters stay bit-identical on both ranks although every rank sees different data"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sync_worker, args=(r, 2, 29651, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=180) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, h0, p0), (_, h1, p1) = res
+    n_small, n_all = 6 * 5 + 5 + 5 * 3 + 3, 6 * 5 + 5 + 5 * 3 + 3 + 5 * 5 + 5
+    assert h0 == h1 == [(n_small, True), (n_all, False), (n_small, True), (n_all, False)]
+    for k in p0:
+        assert p0[k] == p1[k], k
