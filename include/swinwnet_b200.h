@@ -134,14 +134,16 @@ typedef struct swn_param_desc {
   float* p; float* g; float* m; float* v;
   int64_t n;          /* elements */
   int64_t flat_off;   /* element offset of this tensor inside the flat gradient bucket */
+  float bc1, bc2_sqrt; /* AdamW bias corrections 1 - beta1^t, sqrt(1 - beta2^t); t = step count of THIS tensor (torch counts
+                          steps per parameter: a parameter without a gradient in some steps lags behind) */
 } swn_param_desc;
 
 /* torch.optim.AdamW step for ALL parameters in one launch (the optimizer the reference trainers build:
- * FullModel_supervised_trainer.py:85-92): p *= 1 - lr*wd; m, v updates; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps).
+ * FullModel_supervised_trainer.py:85-92): p *= 1 - lr*wd; m, v updates; p -= lr/bc1 * m / (sqrt(v)/bc2_sqrt + eps).
  * `table` = device array of descriptors, `chunks` = device int32 pairs (tensor index, element offset), one CTA per
- * 4096-element chunk; gradients are multiplied by grad_scale first (1/GradScaler scale, or 1). */
+ * 4096-element chunk; tensors with g == NULL are skipped; gradients are multiplied by grad_scale first. */
 int swn_adamw_multi(const swn_param_desc* table, const int32_t* chunks, int n_chunks, double lr, double beta1, double beta2,
-                    double eps, double weight_decay, int step, double grad_scale, void* stream);
+                    double eps, double weight_decay, double grad_scale, void* stream);
 
 /* Data-parallel gradient bucket: unpack=0 gathers every gradient (zeros where g is null) into the flat fp32 bucket that
  * NCCL all-reduces; unpack=1 scatters flat*scale back into the gradients that exist. */

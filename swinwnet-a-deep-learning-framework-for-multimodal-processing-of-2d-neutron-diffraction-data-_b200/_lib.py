@@ -54,8 +54,7 @@ SIGNATURES = {
     "swn_dspace_histogram": (c_int, [c_void_p, c_longlong, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "swn_normalize": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_int, c_void_p]),
     "swn_ensure_2ch": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
-    "swn_adamw_multi": (c_int, [c_void_p, c_void_p, c_int, c_double, c_double, c_double, c_double, c_double, c_int, c_double,
-                                c_void_p]),
+    "swn_adamw_multi": (c_int, [c_void_p, c_void_p, c_int, c_double, c_double, c_double, c_double, c_double, c_double, c_void_p]),
     "swn_grad_bucket_copy": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_double, c_void_p]),
 }
 

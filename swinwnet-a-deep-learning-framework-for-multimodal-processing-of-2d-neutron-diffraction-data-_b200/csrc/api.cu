@@ -210,12 +210,11 @@ int swn_normalize(const float* x, const float* minmax, float* out, int BC, int H
 }
 
 int swn_adamw_multi(const swn_param_desc* table, const int32_t* chunks, int n_chunks, double lr, double beta1, double beta2,
-                    double eps, double weight_decay, int step, double grad_scale, void* stream) {
-  SWN_CHECK(table && chunks && n_chunks > 0 && step >= 1, "adamw_multi: bad arguments");
+                    double eps, double weight_decay, double grad_scale, void* stream) {
+  SWN_CHECK(table && chunks && n_chunks > 0, "adamw_multi: bad arguments");
   static_assert(sizeof(swn_param_desc) == sizeof(AdamWTensor), "swn_param_desc layout");
-  const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
   return launch_adamw_multi(reinterpret_cast<const AdamWTensor*>(table), reinterpret_cast<const int2*>(chunks), n_chunks, (float)lr,
-                            (float)beta1, (float)beta2, (float)eps, (float)weight_decay, (float)bc1, (float)sqrt(bc2), (float)grad_scale,
+                            (float)beta1, (float)beta2, (float)eps, (float)weight_decay, (float)grad_scale,
                             reinterpret_cast<cudaStream_t>(stream));
 }
 

@@ -136,9 +136,10 @@ struct AdamWTensor {      // mirror of swn_param_desc (include/swinwnet_b200.h)
   float* v;               // exp_avg_sq
   long long n;            // elements
   long long flat_off;     // element offset inside the flat all-reduce bucket
+  float bc1, bc2_sqrt;    // 1 - beta1^t, sqrt(1 - beta2^t) with t = this TENSOR's step count (torch keeps it per parameter)
 };
 int launch_adamw_multi(const AdamWTensor* tab, const int2* chunks, int n_chunks, float lr, float beta1, float beta2, float eps,
-                       float wd, float bc1, float bc2_sqrt, float grad_scale, cudaStream_t s);
+                       float wd, float grad_scale, cudaStream_t s);
 int launch_bucket_copy(const AdamWTensor* tab, const int2* chunks, int n_chunks, float* flat, int mode, float scale, cudaStream_t s);
 
 }  // namespace swn

@@ -13,14 +13,14 @@ namespace {
 constexpr int TO_CHUNK = 4096, TO_THREADS = 256;
 
 __global__ void __launch_bounds__(TO_THREADS) adamw_multi_kernel(const AdamWTensor* __restrict__ tab, const int2* __restrict__ chunks,
-                                                                 float lr, float beta1, float beta2, float eps, float wd, float bc1,
-                                                                 float bc2_sqrt, float grad_scale) {
+                                                                 float lr, float beta1, float beta2, float eps, float wd,
+                                                                 float grad_scale) {
   const int2 ch = chunks[blockIdx.x];           // (tensor index, element offset)
   const AdamWTensor t = tab[ch.x];
   if (t.g == nullptr) return;                   // parameter without a gradient this step (frozen / unused branch)
   const long long n = t.n;
   const long long base = ch.y;
-  const float step_size = lr / bc1, decay = 1.0f - lr * wd;
+  const float step_size = lr / t.bc1, decay = 1.0f - lr * wd, bc2_sqrt = t.bc2_sqrt;
   auto upd = [&](float& p, float g, float& m, float& v) {
     g *= grad_scale;
     p *= decay;
@@ -66,9 +66,9 @@ __global__ void __launch_bounds__(TO_THREADS) bucket_copy_kernel(const AdamWTens
 }  // namespace
 
 int launch_adamw_multi(const AdamWTensor* tab, const int2* chunks, int n_chunks, float lr, float beta1, float beta2, float eps,
-                       float wd, float bc1, float bc2_sqrt, float grad_scale, cudaStream_t s) {
+                       float wd, float grad_scale, cudaStream_t s) {
   SWN_CHECK(tab && chunks && n_chunks > 0, "adamw: bad arguments");
-  adamw_multi_kernel<<<n_chunks, TO_THREADS, 0, s>>>(tab, chunks, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt, grad_scale);
+  adamw_multi_kernel<<<n_chunks, TO_THREADS, 0, s>>>(tab, chunks, lr, beta1, beta2, eps, wd, grad_scale);
   SWN_CUDA(cudaGetLastError());
   return 0;
 }

@@ -217,10 +217,10 @@ def dspace_histogram(img, bin_of_pixel, n_bins):
     return out
 
 
-def adamw_multi(table, chunks, n_chunks, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+def adamw_multi(table, chunks, n_chunks, lr, beta1, beta2, eps, weight_decay, grad_scale=1.0):
     """one launch of torch.optim.AdamW semantics over every parameter described by the device table (train.FusedAdamW)."""
     with _Launch(table, chunks) as st:
-        _lib.check(_lib.load().swn_adamw_multi(_ptr(table), _ptr(chunks), n_chunks, lr, beta1, beta2, eps, weight_decay, step,
+        _lib.check(_lib.load().swn_adamw_multi(_ptr(table), _ptr(chunks), n_chunks, lr, beta1, beta2, eps, weight_decay,
                                                grad_scale, st), "swn_adamw_multi")
     _count("adamw_multi")
 

@@ -43,11 +43,12 @@ class _ParamTable:
         self.flat_elems, self.offsets = off, offs
         self.chunks = torch.tensor(chunks, dtype=torch.int32).to(dev)
         self.n_chunks = len(chunks)
-        self._host = torch.zeros(len(self.params), 6, dtype=torch.int64).pin_memory()
-        self._dev = torch.zeros(len(self.params), 6, dtype=torch.int64, device=dev)
+        self._host = torch.zeros(len(self.params), 7, dtype=torch.int64).pin_memory()     # swn_param_desc: 56 bytes
+        self._dev = torch.zeros(len(self.params), 7, dtype=torch.int64, device=dev)
+        self._bc = self._host.view(torch.float32).view(len(self.params), 14)[:, 12:14]    # (bc1, bc2_sqrt) of slot 6
         self._copied = None            # event: the last async H2D copy of the table has consumed the pinned buffer
 
-    def refresh(self, m=None, v=None, grads=None):
+    def refresh(self, m=None, v=None, grads=None, bias_corr=None):
         """(re)write the descriptor table: gradient pointers change from step to step (zero_grad(set_to_none=True))"""
         h = self._host
         if self._copied is not None:
@@ -60,6 +61,8 @@ class _ParamTable:
             h[i, 3] = 0 if v is None else v[i].data_ptr()
             h[i, 4] = p.numel()
             h[i, 5] = self.offsets[i]
+            if bias_corr is not None:
+                self._bc[i, 0], self._bc[i, 1] = bias_corr[i]
         self._dev.copy_(h, non_blocking=True)
         self._copied = torch.cuda.Event()
         self._copied.record(torch.cuda.current_stream(self.device))
@@ -81,7 +84,7 @@ class FusedAdamW(torch.optim.Optimizer):
             v = [torch.zeros_like(p) for p in ps]
             for p, mi, vi in zip(ps, m, v):           # kept in optimizer.state like torch's AdamW (state_dict / release)
                 self.state[p]["exp_avg"], self.state[p]["exp_avg_sq"] = mi, vi
-            t = (key, tab, m, v, [0])
+            t = (key, tab, m, v, [0] * len(ps))
             self._tables[gi] = t
         return t
 
@@ -94,19 +97,22 @@ class FusedAdamW(torch.optim.Optimizer):
         for gi, group in enumerate(self.param_groups):
             if not any(p.requires_grad for p in group["params"]):
                 continue
-            key, tab, m, v, step = self._table(gi, group)
-            grads = []
-            for p in tab.params:
+            key, tab, m, v, steps = self._table(gi, group)
+            b1, b2 = group["betas"]
+            grads, bc = [], []
+            for i, p in enumerate(tab.params):
                 g = p.grad
                 if g is not None and (g.dtype != torch.float32 or not g.is_contiguous()):
                     g = g.float().contiguous()
                 grads.append(g)
+                if g is not None:
+                    steps[i] += 1          # like torch.optim.AdamW: the step count is per parameter
+                t = max(steps[i], 1)
+                bc.append((1.0 - b1 ** t, (1.0 - b2 ** t) ** 0.5))
             if all(g is None for g in grads):
                 continue
-            step[0] += 1
-            b1, b2 = group["betas"]
-            ops.adamw_multi(tab.refresh(m, v, grads), tab.chunks, tab.n_chunks, float(group["lr"]), float(b1), float(b2),
-                            float(group["eps"]), float(group["weight_decay"]), step[0], 1.0)
+            ops.adamw_multi(tab.refresh(m, v, grads, bc), tab.chunks, tab.n_chunks, float(group["lr"]), float(b1), float(b2),
+                            float(group["eps"]), float(group["weight_decay"]), 1.0)
         return loss
 
 

@@ -12,7 +12,8 @@ from oracle import swinwnet_oracle as O
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
-TOL = 2e-2
+BF16 = S.ops.operand_dtype() == torch.bfloat16     # non-default build variant: characterisation bounds (see test_gpu_gates.py)
+TOL = 6e-2 if BF16 else 2e-2
 D2 = [2, 2, 2, 2]
 
 
@@ -253,10 +254,10 @@ def test_acceptance_gates_surrogate_checkpoint(surrogate):
     for n, a, b in (("LR", c[0], o[0]), ("HR", c[6], o[6])):
         agree = ((torch.sigmoid(a) >= 0.5) == (torch.sigmoid(b) >= 0.5)).float().mean().item()
         print(f"mask agreement {n}: {agree:.6f}  (foreground fraction {(torch.sigmoid(b) >= 0.5).float().mean().item():.3f})")
-        assert agree >= 0.999, (n, agree)
+        assert agree >= (0.995 if BF16 else 0.999), (n, agree)
     p_c, p_o = psnr(c[2], o[4]), psnr(o[2], o[4])
     print("PSNR cuda / oracle:", p_c, p_o)
-    assert abs(p_c - p_o) <= 0.05
+    assert abs(p_c - p_o) <= (0.2 if BF16 else 0.05)
     m_c = DM.physical_metrics(c[3].numpy(), o[1].numpy())
     m_o = DM.physical_metrics(o[3].numpy(), o[1].numpy())
     # Conditioning of the gauge itself: the metric goes through scipy.find_peaks thresholds and integer peak windows
@@ -277,4 +278,4 @@ def test_acceptance_gates_surrogate_checkpoint(surrogate):
     for k in ("Integral Intensity", "Peak Intensity"):
         a, b = float(np.mean(np.asarray(m_c[k])[stable])), float(np.mean(np.asarray(m_o[k])[stable]))
         print(k, "cuda / oracle:", a, b, "per-sample", m_c[k], m_o[k])
-        assert b > 0 and abs(a - b) <= 0.01 * abs(b), (k, a, b)
+        assert b > 0 and abs(a - b) <= (0.05 if BF16 else 0.01) * abs(b), (k, a, b)
