@@ -23,6 +23,14 @@
 #ifndef SWN_FUSED_SPIN
 #define SWN_FUSED_SPIN 0
 #endif
+// 1 = token rows of swin_fused_kernel move through the TMA engine (one cp.async.bulk per row global -> staging and
+// staging -> global, issued by the 128 lanes of warps 4-7).  MEASURED SLOWER at these row sizes (48 / 96 / 192 bytes: per-copy
+// overhead of the TMA engine; C = 48: 0.88 vs 0.77 ms, C = 12: 4.91 vs 4.15 ms, gpurun_out/r2g_ops.txt), so the 16-byte
+// cp.async gather / float4 write-back stays the product path; at 384-byte rows (swin_attn_stream_kernel, C = 96) the
+// bulk gather wins 10 % and is unconditional there.
+#ifndef SWN_FUSED_BULK
+#define SWN_FUSED_BULK 0
+#endif
 
 namespace swn {
 
@@ -49,7 +57,7 @@ __device__ __forceinline__ uint32_t fb_exp2_pack(float a, float b, float m) {
 }
 
 struct FbBars {
-  uint64_t w, mma, g1[2], g2[2];
+  uint64_t w, mma, g1[2], g2[2], rows[2];
   uint32_t tmem_base;
 };
 
@@ -229,6 +237,8 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
     mbar_init(&bars->g1[1], 1);
     mbar_init(&bars->g2[0], 1);
     mbar_init(&bars->g2[1], 1);
+    mbar_init(&bars->rows[0], 128);
+    mbar_init(&bars->rows[1], 128);
     fence_barrier_init();
   }
   for (int i = tid * 16; i < KB * A_KBLOCK_BYTES; i += NT * 16) *reinterpret_cast<uint4*>(a_s + i) = make_uint4(0u, 0u, 0u, 0u);
@@ -272,6 +282,20 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
   const int ch_r0 = tid / C4, ch_c0 = tid - ch_r0 * C4;
   constexpr int ch_rstep = NT / C4, ch_cstep = NT - ch_rstep * C4;
   auto issue_loads = [&](int slot, int buf) {
+#if SWN_FUSED_BULK
+    if (warp >= 4 && warp < 8) {
+      const int r = tid - 128;
+      bulk_wait_read();            // this lane's write-back of the tile that used the buffer has left shared memory
+      const int tok = tok_s[slot * 128 + r];
+      if (tok >= 0) {
+        mbar_arrive_expect_tx(&bars->rows[buf], (uint32_t)(C * 4));
+        bulk_g2s(stg + buf * 128 * RSB + r * RSB, p.x + (long long)tok * C, (uint32_t)(C * 4), &bars->rows[buf]);
+      } else {
+        mbar_arrive(&bars->rows[buf]);   // rows of invalid tokens keep stale bytes: every consumer masks them (tok < 0)
+      }
+    }
+    return;
+#endif
     const uint32_t dst0 = smem_u32(stg + buf * 128 * RSB);
     int r = ch_r0, c4 = ch_c0;
     while (r < 128) {
@@ -341,6 +365,7 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
     ph_t = clock64();
   }
   const bool prefetch = p.n_stage == 2;
+  uint32_t rows_ph = 0;        // phase parity of rows[0] / rows[1], one bit each
   calc_tok(blockIdx.x, 0);     // grid <= ntiles
   __syncthreads();
   if (prefetch) issue_loads(0, 0);
@@ -352,6 +377,15 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
     if (has_next) calc_tok(next, (it + 1) % 3);
     __syncthreads();   // previous tile's write-back finished everywhere; tok of the next tile visible
     mark(0);
+#if SWN_FUSED_BULK
+    if (prefetch) {
+      if (has_next) issue_loads((it + 1) % 3, buf ^ 1);
+    } else {
+      issue_loads(slot, 0);
+    }
+    mbar_wait(&bars->rows[buf], (rows_ph >> buf) & 1u);   // this tile's rows are in stg[buf]
+    rows_ph ^= 1u << buf;
+#else
     if (prefetch) {
       if (has_next) {
         issue_loads((it + 1) % 3, buf ^ 1);
@@ -364,6 +398,7 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
       asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();   // this tile's rows are in stg[buf]
+#endif
     mark(1);
 
     uint8_t* stile = stg + buf * 128 * RSB;
@@ -509,6 +544,9 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
       red[part * 128 + row] = make_float2(s1, s2);
     }
     tc_fence_before();
+#if SWN_FUSED_BULK
+    if (!p.do_mlp) fence_proxy_async();   // the staged rows are the result: read by the bulk write-back (async proxy)
+#endif
     __syncthreads();
     mark(8);
 
@@ -675,11 +713,22 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
         }
       }
       tc_fence_before();
+#if SWN_FUSED_BULK
+      fence_proxy_async();
+#endif
       __syncthreads();
       mark(15);
     }
 
-    // ---------------- coalesced write-back of the valid token rows ----------------
+    // ---------------- write-back of the valid token rows ----------------
+#if SWN_FUSED_BULK
+    if (warp >= 4 && warp < 8) {
+      const int r = tid - 128;
+      const int tok = tok_s[slot * 128 + r];
+      if (tok >= 0) bulk_s2g(p.out + (long long)tok * C, stile + r * RSB, (uint32_t)(C * 4));
+      bulk_commit();
+    }
+#else
     {
       int r = ch_r0, c4 = ch_c0;
       while (r < 128) {
@@ -694,10 +743,14 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
         }
       }
     }
+#endif
   }
 
   if constexpr (PROF) if (prof)
     for (int i = 0; i < 16; ++i) p.phase_cycles[(long long)blockIdx.x * 16 + i] += ph_acc[i];
+#if SWN_FUSED_BULK
+  bulk_wait_all();             // outstanding write-backs read this CTA's shared memory
+#endif
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -722,7 +775,7 @@ __global__ void __launch_bounds__(NT, MINB) swin_fused_kernel(const FusedBlockPa
 // =================================================================================================================
 namespace {
 struct FsBars {
-  uint64_t full[4], mma;
+  uint64_t full[4], mma, rows;
   uint32_t tmem_base;
 };
 constexpr int FS_C = 96, FS_K16 = 96, FS_ONES = 288, FS_NQ = 304, FS_NQ0 = 160, FS_NQ1 = 144, FS_RS = 312;
@@ -757,6 +810,7 @@ __global__ void __launch_bounds__(512, 1) swin_attn_stream_kernel(const FusedBlo
   if (tid == 0) {
     for (int i = 0; i < FS_NSTG; ++i) mbar_init(&bars->full[i], 1);
     mbar_init(&bars->mma, 1);
+    mbar_init(&bars->rows, 128);
     fence_barrier_init();
   }
   for (int i = tid * 16; i < 2 * A_KBLOCK_BYTES + FS_U_BYTES; i += NT * 16) *reinterpret_cast<uint4*>(a_s + i) = make_uint4(0u, 0u, 0u, 0u);
@@ -805,18 +859,24 @@ __global__ void __launch_bounds__(512, 1) swin_attn_stream_kernel(const FusedBlo
       tok_s[slot * 128 + tid] = tok;
     }
   };
-  // gather the fp32 rows of a tile into the staging view of u_s ([128][FS_RSX] bytes); zero-fill for invalid tokens
+  // gather the fp32 rows of a tile into the staging view of u_s ([128][FS_RSX] bytes): ONE bulk copy (TMA engine) per
+  // token row, issued by the 128 lanes of warps 4-7 — no LSU instructions, no address math in the other warps (the
+  // 16-byte cp.async gather this replaces cost 15 % of a tile: 3072 LDGSTS per tile through the LSU pipe).  Every lane
+  // arrives once on `rows` (count 128), valid rows add their 384 bytes to the transaction count; rows of invalid tokens
+  // keep stale bytes, which every consumer masks with tok >= 0.
   auto issue_loads = [&](int slot) {
-    const uint32_t dst0 = smem_u32(u_s);
-#pragma unroll
-    for (int i = 0; i < 128 * (C / 4) / NT; ++i) {
-      const int q = tid + i * NT, r = q / (C / 4), c4 = q - r * (C / 4);
+    if (warp >= 4 && warp < 8) {
+      const int r = tid - 128;
       const int tok = tok_s[slot * 128 + r];
-      const float* src = tok >= 0 ? p.x + (long long)tok * C + c4 * 4 : p.x;
-      cp_async16(dst0 + r * FS_RSX + c4 * 16, src, tok >= 0 ? 16u : 0u);
+      if (tok >= 0) {
+        mbar_arrive_expect_tx(&bars->rows, (uint32_t)(C * 4));
+        bulk_g2s(u_s + r * FS_RSX, p.x + (long long)tok * C, (uint32_t)(C * 4), &bars->rows);
+      } else {
+        mbar_arrive(&bars->rows);
+      }
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
   };
+  uint32_t ph_rows = 0;
   uint32_t ph_mma = 0;
   push(4);                      // the first tile's qkv weights
   calc_tok(blockIdx.x, 0);      // grid <= ntiles
@@ -845,8 +905,8 @@ __global__ void __launch_bounds__(512, 1) swin_attn_stream_kernel(const FusedBlo
     const bool has_next = next < p.ntiles;
     const int tokr = tok_s[slot * 128 + row];
     // ---------------- LN1 from the staged rows: this thread owns the 16-column units {part, part + 4} ----------
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
+    mbar_wait(&bars->rows, ph_rows);
+    ph_rows ^= 1u;
     mark(0);
     float xv[2][16];
     constexpr int NU = C / 16;   // 6 units per row
