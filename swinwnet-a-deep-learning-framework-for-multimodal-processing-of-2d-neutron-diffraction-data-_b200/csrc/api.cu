@@ -27,7 +27,11 @@ static void mlp_config(int C, int* HC, int* TR) {
   // columns — measured 13 % faster than two 64-column accumulators: 0.60 -> 0.52 ms at M = 122 880)
   (void)hbase;
   if (C > 96 && Hd % 128 == 0) *HC = 128;
+#ifdef SWN_MLP96_HC
+  else if (C == 96) *HC = SWN_MLP96_HC;
+#else
   else if (C == 96) *HC = 96;              // persistent kernel: 4 chunks of 96 measured 5 % faster than 6 of 64
+#endif
   else if (Hd % 64 == 0) *HC = 64;
   else *HC = Hd;
   *TR = C16 <= 256 ? C16 : (C16 % 128 == 0 ? 128 : C16 / 2);

@@ -42,7 +42,10 @@ namespace swn {
 #define MP_TIMED(slot, stmt) do { stmt; } while (0)
 #endif
 
-constexpr int MP_EPI_SPLIT = 2;                 // epilogue warps per TMEM lane group (they split the columns)
+#ifndef SWN_MP_EPI_SPLIT
+#define SWN_MP_EPI_SPLIT 2
+#endif
+constexpr int MP_EPI_SPLIT = SWN_MP_EPI_SPLIT;  // epilogue warps per TMEM lane group (they split the columns)
 constexpr int MP_WARPS = 8 + 4 * MP_EPI_SPLIT;
 constexpr int MP_THREADS = MP_WARPS * 32;
 constexpr int MP_LN_WARPS = 4;

@@ -324,3 +324,66 @@ def test_runs_on_a_non_current_device(manifest):
     assert torch.equal(a, b)
     with pytest.raises(RuntimeError, match="different devices"):
         ops.normalize(x.to("cuda:0"), torch.zeros(2, 2, device="cuda:1"), inverse=False)
+
+
+# ---------------------------------------------------------------------------------------------
+# compute-sanitizer is closed on this GPU pool (profiles/r2_compute_sanitizer_closed.txt), so the memcheck / racecheck
+# runs SURVEY.md §5 asks for are replaced by what can be checked from the outside: guard bands around every output
+# (out-of-bounds writes), NaN-prefilled outputs (unwritten elements) and bit-identical repeated launches of the
+# persistent kernels with many tiles per CTA (a shared-memory / mbarrier race shows up as run-to-run differences).
+# ---------------------------------------------------------------------------------------------
+def _guarded(shape, dtype=torch.float32, pad=4096):
+    n = 1
+    for s in shape:
+        n *= s
+    buf = torch.full((n + 2 * pad,), 12345.0, device=DEV, dtype=dtype)
+    view = buf[pad:pad + n].view(*shape)
+    view.fill_(float("nan"))
+    return buf, view, pad
+
+
+def _guards_intact(buf, pad):
+    return bool((buf[:pad] == 12345.0).all() and (buf[-pad:] == 12345.0).all())
+
+
+@pytest.mark.parametrize("C,nH,B,H,W", [(12, 3, 2, 123, 241), (24, 3, 2, 63, 121), (48, 6, 3, 62, 99), (96, 3, 3, 62, 99), (96, 6, 5, 63, 120)])
+def test_fused_kernels_guard_bands_and_repeatability(C, nH, B, H, W):
+    x = rnd(B, H * W, C, seed=1)
+    sd = _block_sd(C, nH)
+    whole = C < 96
+    pk = (packing.pack_fused_block(*[sd[k] for k in sd], nH) if whole else
+          packing.pack_fused_attn_stream(*[sd[k] for k in list(sd)[:7]], nH))
+    ref = None
+    for rep in range(6):
+        buf, out, pad = _guarded((B, H * W, C))
+        ops.swin_block_fused(x, out, B, H, W, C, nH, 1e-5, pk[0], pk[1], whole)
+        torch.cuda.synchronize()
+        assert _guards_intact(buf, pad) and torch.isfinite(out).all()
+        ref = out.clone() if ref is None else ref
+        assert torch.equal(out, ref), f"launch {rep} differs from launch 0"
+
+
+@pytest.mark.parametrize("C", [48, 96, 192, 384])
+def test_mlp_and_rowgemm_guard_bands_and_repeatability(C):
+    M = 128 * _sms() * 3 + 37
+    x = rnd(M, C, seed=1)
+    W1, b1 = rnd(4 * C, C, seed=2, scale=C ** -0.5), rnd(4 * C, seed=3, scale=0.2)
+    W2, b2 = rnd(C, 4 * C, seed=4, scale=(4 * C) ** -0.5), rnd(C, seed=5, scale=0.1)
+    lw, lb = 1 + 0.1 * rnd(C, seed=6), 0.1 * rnd(C, seed=7)
+    HC, TR = ops.mlp_config(C)
+    Wp, b2p = packing.pack_mlp(W1, W2, b2, HC, TR)
+    Wq, bq = rnd(3 * C, C, seed=8, scale=C ** -0.5), rnd(3 * C, seed=9, scale=0.1)
+    nv = packing.choose_chunk(3 * C, 128 if C <= 192 else 256)
+    Wqp, bqp, NT, nch = packing.pack_rowgemm(Wq, bq, nv)
+    ref_m = ref_q = None
+    for rep in range(5):
+        buf, out, pad = _guarded((M, C))
+        ops.mlp(x, out, M, C, lw, lb, Wp, b1, b2p)
+        bq2, qkv, pad2 = _guarded((M, 3 * C), dtype=OPD)
+        ops.rowgemm(A=x, a_mode=ops.A_F32_LN, M=M, K=C, lda=C, ln_w=lw, ln_b=lb, Wp=Wqp, NT=NT, nchunks=nch, n_valid=nv,
+                    e_mode=ops.E_BF16, bias=bqp, out=qkv, ldo=3 * C)
+        torch.cuda.synchronize()
+        assert _guards_intact(buf, pad) and _guards_intact(bq2, pad2)
+        assert torch.isfinite(out).all() and torch.isfinite(qkv.float()).all()
+        ref_m, ref_q = (out.clone(), qkv.clone()) if ref_m is None else (ref_m, ref_q)
+        assert torch.equal(out, ref_m) and torch.equal(qkv, ref_q), f"launch {rep} differs from launch 0"
