@@ -156,7 +156,7 @@ def library_bar(dev, batches=(8, 64), iters=3):
     """the unmodified reference on THIS GPU (eager ATen / cuBLAS): the bar a hand-written path has to clear."""
     try:
         import library_bar as LB
-        r = LB.measure(batches=batches, modes=("fp32", "tf32", "bf16_autocast"), iters=iters, device=str(dev))
+        r = LB.measure(batches=batches, modes=("fp32", "tf32", "bf16_autocast"), iters=iters, device=str(dev), verbose=False)
     except Exception as e:
         return {"unavailable": f"{type(e).__name__}: {str(e)[:160]}"}
     best = {}
@@ -307,7 +307,7 @@ def parity_check(inf, x_dev, sd, two_channel=True):
     the upscaled image and the final output, gate 2e-2); (2) against a solo B=1 run of the same sample (bit-equal)."""
     from oracle import swinwnet_oracle as O
     B = x_dev.shape[0]
-    full = inf(x_dev)
+    full = inf(x_dev, two_channel)
     keys = ("seg_lr_logits", "upscaled_norm", "seg_hr_logits", "images_masked_hr")
     got = {k: getattr(inf, k).clone() for k in keys}
     idx = sorted({0, B - 1})
@@ -320,7 +320,7 @@ def parity_check(inf, x_dev, sd, two_channel=True):
                 e = (a - b).abs().max().item() / max(b.abs().max().item(), 1e-6)
                 per[f"{k}[{i}]"] = e
                 worst = max(worst, e if torch.isfinite(a).all() else float("inf"))
-            solo = inf(x_dev[i:i + 1], two_channel) if not two_channel else inf(x_dev[i:i + 1])
+            solo = inf(x_dev[i:i + 1], two_channel)
             bit_equal &= bool(torch.equal(solo, got["images_masked_hr"][i:i + 1]))
     del full
     return {"samples": idx, "max_rel": worst, "tol": 2e-2, "bit_equal_vs_solo": bit_equal, "per_tensor": per,

@@ -229,3 +229,26 @@ def test_gelu_pack2_half_pipeline_error_budget():
         one_rounding = exact.astype(f16).astype(np.float64)
         assert (got - exact).std() <= 1.8 * (one_rounding - exact).std() + 1e-6
         assert np.abs(got - exact).max() <= 2.5e-3 * max(1.0, sd)
+
+
+def test_npy_batch_ingestion_and_pathlike_checkpoint(tmp_path):
+    """f-4: .npy batches in the viewer's formats (2-D / 3-D / 4-D arrays, dict files) -> [B,C,H,W]; checkpoints given as
+    pathlib.Path."""
+    import numpy as np
+    from swinwnet_b200 import checkpoint as CK
+    a2, a3 = np.random.rand(6, 8).astype(np.float32), np.random.rand(3, 6, 8)
+    np.save(tmp_path / "one.npy", a2)
+    np.save(tmp_path / "three.npy", a3)
+    np.save(tmp_path / "d.npy", {"images": np.random.rand(2, 1, 6, 8), "other": 1}, allow_pickle=True)
+    x = CK.load_npy_batch([tmp_path / "one.npy", tmp_path / "three.npy", tmp_path / "d.npy"], pin=False)
+    assert x.shape == (6, 1, 6, 8) and x.dtype == torch.float32
+    assert torch.equal(x[0, 0], torch.from_numpy(a2)) and torch.allclose(x[1:4, 0], torch.from_numpy(a3).float())
+    np.save(tmp_path / "bad.npy", np.zeros((2, 5, 8)))
+    with pytest.raises(ValueError):
+        CK.load_npy_batch([tmp_path / "one.npy", tmp_path / "bad.npy"], pin=False)
+    with pytest.raises(ValueError):
+        CK.as_4d(np.zeros((1, 2, 3, 4, 5)))
+    m = S.SwinUNet(depths=[2, 2, 2, 2])
+    torch.save({"state_dict": {"module." + k: v for k, v in m.state_dict().items()}}, tmp_path / "ck.pth")
+    m2 = CK.build_model_from_checkpoint(tmp_path / "ck.pth")           # pathlib.Path
+    assert type(m2).__name__ == "SwinUNet" and len(m2.state_dict()) == len(m.state_dict())

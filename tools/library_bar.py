@@ -18,7 +18,7 @@ import benchdata  # noqa: E402
 from stage_reference import import_reference  # noqa: E402
 
 
-def measure(batches=(1, 8, 64), modes=("fp32", "tf32", "bf16_autocast", "fp16_autocast"), iters=5, device="cuda:0"):
+def measure(batches=(1, 8, 64), modes=("fp32", "tf32", "bf16_autocast", "fp16_autocast"), iters=5, device="cuda:0", verbose=True):
     ref_dir, R, P = import_reference()
     man = json.load(open(os.path.join(ROOT, "tests", "golden", "manifest.json")))
     model = R.SwinWNet(error_matrix=True, depths=[2, 2, 2, 2])
@@ -55,7 +55,8 @@ def measure(batches=(1, 8, 64), modes=("fp32", "tf32", "bf16_autocast", "fp16_au
                 res["runs"].append({"batch": B, "mode": mode, "error": f"{type(e).__name__}: {str(e)[:200]}"})
             torch.cuda.reset_peak_memory_stats()
             torch.cuda.empty_cache()
-            print(res["runs"][-1], flush=True)
+            if verbose:
+                print(res["runs"][-1], flush=True)
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = True
     return res
