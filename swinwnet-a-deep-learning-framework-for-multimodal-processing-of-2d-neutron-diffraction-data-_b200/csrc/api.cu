@@ -44,16 +44,19 @@ static void mlp_config(int C, int* HC, int* TR) {
 #endif
 }
 static long long* g_phase_cycles = nullptr;
+#ifndef SWN_MLP_PERSIST_MAX_C_DEFAULT
+#define SWN_MLP_PERSIST_MAX_C_DEFAULT 96   // 192 routes C = 192 through the DIRECT (global-read LayerNorm) persistent variant
+#endif
 static int mlp_persist_max_c() {
 #if SWN_TUNING_HOOKS
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("SWN_MLP_PERSIST_MAX_C");
-    v = e ? atoi(e) : 96;
+    v = e ? atoi(e) : SWN_MLP_PERSIST_MAX_C_DEFAULT;
   }
   return v;
 #else
-  return 96;   // the DIRECT variant (C = 192) is correct but measured 9 % slower than mlp.cu so far
+  return SWN_MLP_PERSIST_MAX_C_DEFAULT;
 #endif
 }
 static int num_sms() {

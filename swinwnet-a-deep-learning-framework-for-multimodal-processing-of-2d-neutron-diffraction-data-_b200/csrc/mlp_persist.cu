@@ -55,7 +55,7 @@ struct MpSmem {
   uint64_t full[8], empty[8];
   uint64_t in_full[2], in_empty[2];
   uint64_t hacc_full[2], hacc_empty[2], hs_full[2], hs_empty[2];
-  uint64_t a_full, a_empty, y_full, y_empty;
+  uint64_t a_full[2], a_empty[2], y_full, y_empty;    // DIRECT: two A tiles (LayerNorm of tile i+1 overlaps the GEMMs of tile i)
   uint32_t tmem_base;
 };
 
@@ -76,8 +76,11 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
   const int w1_bytes = HC * 128, w2_bytes = TR * 128;
   const int rs = p.row_stride;  // staging row stride in bytes (odd number of 16-byte chunks)
 
+  constexpr int NA = DIRECT ? 2 : 1;                   // A-tile buffers
+  constexpr int LN_FIRST = DIRECT ? 2 : 4;             // DIRECT: no input producer -> warps 2..7 run the LayerNorm prologue
+  constexpr int LN_WARPS = DIRECT ? 6 : MP_LN_WARPS;
   uint8_t* a_smem = smem;
-  uint8_t* hs_smem = a_smem + KB1 * A_KBLOCK_BYTES;
+  uint8_t* hs_smem = a_smem + NA * KB1 * A_KBLOCK_BYTES;
   uint8_t* ring = hs_smem + 2 * nkk * A_KBLOCK_BYTES;
   uint8_t* stg = ring + p.stages * stage_bytes;                     // 2 x [128 x rs]
   float* b1s = reinterpret_cast<float*>(stg + 2 * TILE_M * rs);     // [4C]
@@ -103,8 +106,10 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
       mbar_init(&sh->hs_full[b], MP_EPI_THREADS / 32);
       mbar_init(&sh->hs_empty[b], 1);
     }
-    mbar_init(&sh->a_full, MP_LN_WARPS);
-    mbar_init(&sh->a_empty, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&sh->a_full[b], LN_WARPS);
+      mbar_init(&sh->a_empty[b], 1);
+    }
     mbar_init(&sh->y_full, 1);
     mbar_init(&sh->y_empty, MP_EPI_THREADS / 32);
     fence_barrier_init();
@@ -170,6 +175,8 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int g0 = it * nj;  // global chunk counter of this tile's first chunk
+      const int ab = NA == 2 ? (it & 1) : 0;                       // A buffer of this tile
+      const uint32_t aph = NA == 2 ? (((uint32_t)it >> 1) & 1u) : ((uint32_t)it & 1u);
       auto gemm1 = [&](int j) {
         const int g = g0 + j, buf = g & 1;
         MP_TIMED(2, mbar_wait(&sh->hacc_empty[buf], (((uint32_t)g >> 1) & 1u) ^ 1u));
@@ -178,7 +185,7 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
           MP_TIMED(1, mbar_wait(&sh->full[rp.s], rp.ph));
           tc_fence_after();
           if (elect_one()) {
-            const uint64_t ad = a_desc0 + (uint64_t)(kb * kblk_d16), bd = ring_desc0 + (uint64_t)(rp.s * stage_d16);
+            const uint64_t ad = a_desc0 + (uint64_t)((ab * KB1 + kb) * kblk_d16), bd = ring_desc0 + (uint64_t)(rp.s * stage_d16);
             const int steps = min(4, steps1 - kb * 4);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
@@ -186,7 +193,7 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
             umma_commit(&sh->empty[rp.s]);
             if (kb == KB1 - 1) {
               umma_commit(&sh->hacc_full[buf]);
-              if (j == nj - 1) umma_commit(&sh->a_empty);  // A tile free once the last GEMM1 retires
+              if (j == nj - 1) umma_commit(&sh->a_empty[ab]);  // A tile free once the last GEMM1 retires
             }
           }
           __syncwarp();
@@ -219,14 +226,14 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
           }
         }
       };
-      MP_TIMED(0, mbar_wait(&sh->a_full, (uint32_t)it & 1u));
+      MP_TIMED(0, mbar_wait(&sh->a_full[ab], aph));
       gemm1(0);
       for (int j = 0; j < nj; ++j) {
         if (j + 1 < nj) gemm1(j + 1);
         gemm2(j);
       }
     }
-  } else if (warp >= 4 && warp < 4 + MP_LN_WARPS) {
+  } else if (warp >= LN_FIRST && warp < LN_FIRST + LN_WARPS) {
     // ===== LayerNorm warps: staging (fp32) -> A tile (bf16, swizzled) =====
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
@@ -235,19 +242,22 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
       const int rows = (int)min((long long)TILE_M, (long long)p.M - m0);
       if (DIRECT) {
         // rows straight from global memory, lanes along the row (coalesced), 4 rows in flight per warp
-        mbar_wait(&sh->a_empty, ((uint32_t)it & 1u) ^ 1u);
+        const int ab = it & 1;
+        mbar_wait(&sh->a_empty[ab], (((uint32_t)it >> 1) & 1u) ^ 1u);
         const float* xg = p.x;
-        build_a_tile<32, (LPR == 32 ? 2 : 1), 4, true>(a_smem, C, C16, p.ln_w, p.ln_b, p.ln_eps, warp - 4, MP_LN_WARPS, lane, [&](int r, int k) {
+        // 6 rows in flight per warp (12 float4 per lane): with 4 the prologue was bound by global-load latency (29 k
+        // cycles per tile, profiles/r2_mlp_direct_role_waits.txt)
+        build_a_tile<32, (LPR == 32 ? 2 : 1), 6, true>(a_smem + ab * KB1 * A_KBLOCK_BYTES, C, C16, p.ln_w, p.ln_b, p.ln_eps, warp - LN_FIRST, LN_WARPS, lane, [&](int r, int k) {
           const long long mr = m0 + r;
           if (mr >= p.M) return make_float4(0.f, 0.f, 0.f, 0.f);
           return __ldg(reinterpret_cast<const float4*>(xg + mr * C + k));
         });
         fence_proxy_async();
-        mbar_arrive_warp(&sh->a_full);
+        mbar_arrive_warp(&sh->a_full[ab]);
         continue;
       }
-      if (warp == 4) { MP_TIMED(12, mbar_wait(&sh->in_full[s], ((uint32_t)it >> 1) & 1u)); MP_TIMED(13, mbar_wait(&sh->a_empty, ((uint32_t)it & 1u) ^ 1u)); }
-      else { mbar_wait(&sh->in_full[s], ((uint32_t)it >> 1) & 1u); mbar_wait(&sh->a_empty, ((uint32_t)it & 1u) ^ 1u); }
+      if (warp == 4) { MP_TIMED(12, mbar_wait(&sh->in_full[s], ((uint32_t)it >> 1) & 1u)); MP_TIMED(13, mbar_wait(&sh->a_empty[0], ((uint32_t)it & 1u) ^ 1u)); }
+      else { mbar_wait(&sh->in_full[s], ((uint32_t)it >> 1) & 1u); mbar_wait(&sh->a_empty[0], ((uint32_t)it & 1u) ^ 1u); }
       const long long t_ln0 = SWN_MLP_PROFILE ? clock64() : 0;
       // one thread per row (the staging rows are padded to an odd number of 16-byte chunks, so this is bank
       // conflict free): no shuffles, long independent instruction streams.  Shifted one-pass moments.
@@ -295,7 +305,7 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
         *reinterpret_cast<uint4*>(a_smem + (k >> 6) * A_KBLOCK_BYTES + sw128_offset(row, k & 63)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
       fence_proxy_async();
-      mbar_arrive_warp(&sh->a_full);
+      mbar_arrive_warp(&sh->a_full[0]);
 #if SWN_MLP_PROFILE
       if (p.phase_cycles && warp == 4 && lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.phase_cycles + 14), (unsigned long long)(clock64() - t_ln0));
 #endif
@@ -379,14 +389,19 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
             xr[ps] = (cb < (C16 >> 4) && c < C && mm < p.M) ? __ldg(reinterpret_cast<const float4*>(p.x + mm * C + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         };
-        float4 xr_cur[4], xr_nxt[4];
-        load_res(part, xr_cur);
+        // residual rows (L2 hits: the LayerNorm warps read them one tile earlier) are requested TWO column blocks ahead
+        float4 cur[4], nx1[4], nx2[4];
+        load_res(part, cur);
+        load_res(part + MP_EPI_SPLIT, nx1);
         for (int cb = part; cb < (C16 >> 4); cb += MP_EPI_SPLIT) {
-          load_res(cb + MP_EPI_SPLIT, xr_nxt);
+          load_res(cb + 2 * MP_EPI_SPLIT, nx2);
           tmem_ld16(lane_addr + (uint32_t)(cb * 16), v);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] += b2s[cb * 16 + j];
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 bb = *reinterpret_cast<const float4*>(b2s + cb * 16 + j4 * 4);
+            v[j4 * 4] += bb.x; v[j4 * 4 + 1] += bb.y; v[j4 * 4 + 2] += bb.z; v[j4 * 4 + 3] += bb.w;
+          }
           epi_scatter16(scr, v, lane);
           const int c = cb * 16 + (lane & 3) * 4;
           if (c < C) {
@@ -395,11 +410,14 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
               const long long mm = (long long)tile * TILE_M + lg * 32 + ps * 8 + (lane >> 2);
               if (mm >= p.M) continue;
               const float4 y = epi_gather4(scr, ps, lane);
-              *reinterpret_cast<float4*>(p.out + mm * C + c) = make_float4(y.x + xr_cur[ps].x, y.y + xr_cur[ps].y, y.z + xr_cur[ps].z, y.w + xr_cur[ps].w);
+              *reinterpret_cast<float4*>(p.out + mm * C + c) = make_float4(y.x + cur[ps].x, y.y + cur[ps].y, y.z + cur[ps].z, y.w + cur[ps].w);
             }
           }
 #pragma unroll
-          for (int ps = 0; ps < 4; ++ps) xr_cur[ps] = xr_nxt[ps];
+          for (int ps = 0; ps < 4; ++ps) {
+            cur[ps] = nx1[ps];
+            nx1[ps] = nx2[ps];
+          }
           __syncwarp();
         }
       } else {
@@ -465,7 +483,7 @@ int launch_mlp_persist(MlpParams p, int num_sms, cudaStream_t stream) {
   const int chunks = C / 4;
   p.row_stride = direct ? 0 : (chunks + ((chunks & 1) ? 0 : 1)) * 16;
   const int stage_bytes = (p.HC > p.TR ? p.HC : p.TR) * 128;
-  const int fixed = 1024 + (KB1 + 2 * nkk) * A_KBLOCK_BYTES + 2 * TILE_M * p.row_stride + (4 * C + 3 * C16) * 4 +
+  const int fixed = 1024 + ((direct ? 2 : 1) * KB1 + 2 * nkk) * A_KBLOCK_BYTES + 2 * TILE_M * p.row_stride + (4 * C + 3 * C16) * 4 +
                     (int)sizeof(MpSmem) + 64 + (direct ? 8 * EPI_SCRATCH_BYTES + 16 : 0);
   int stages = (232448 - fixed) / stage_bytes;
   if (stages > 6) stages = 6;
