@@ -100,17 +100,11 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(const MlpParams p) 
       mbar_init(&sh->hs_full[b], MLP_EPI_THREADS / 32);
       mbar_init(&sh->hs_empty[b], 1);
     }
-    mbar_init(&sh->a_ready, MLP_WARPS);
     mbar_init(&sh->y_full, 1);
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < 4 * C; i += MLP_THREADS) b1s[i] = p.b1[i];
   for (int i = threadIdx.x; i < C16; i += MLP_THREADS) b2s[i] = p.b2[i];
-  if (warp == 0) tmem_alloc(&sh->tmem_base, (uint32_t)p.tmem_cols);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = sh->tmem_base;
 
   // ---- weight stream bookkeeping (consumption order: G1(0), [G1(j+1), G2(j)]..., G2(nj-1)) ----
   // tile t -> byte size: tiles [0,KB1) are W1; then per j: (j+1<nj ? KB1 W1 tiles : none) + nkk*nT W2 tiles
@@ -132,29 +126,39 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(const MlpParams p) 
       }
     }
   };
-  if (threadIdx.x == 0) {   // first ring fill before the prologue (no empty-wait needed)
-    for (; pt < p.stages; ++pt) {
-      const int bytes = next_bytes();
-      if (bytes == 0) break;
-      mbar_arrive_expect_tx(&sh->full[pt], (uint32_t)bytes);
-      bulk_g2s(ring + pt * stage_bytes, wsrc, (uint32_t)bytes, &sh->full[pt]);
-      wsrc += bytes;
+  // Per-CTA setup runs in warp 0 WHILE warps 1.. build the A tile (the kernel is not persistent; with tcgen05.alloc and
+  // the barrier in front of the prologue every CTA paid them serially): first ring fill (issued by the thread that
+  // initialised the barriers: program order), then the TMEM allocation.
+  if (warp == 0) {
+    if (lane == 0) {
+      for (; pt < p.stages; ++pt) {
+        const int bytes = next_bytes();
+        if (bytes == 0) break;
+        mbar_arrive_expect_tx(&sh->full[pt], (uint32_t)bytes);
+        bulk_g2s(ring + pt * stage_bytes, wsrc, (uint32_t)bytes, &sh->full[pt]);
+        wsrc += bytes;
+      }
     }
+    __syncwarp();
+    tmem_alloc(&sh->tmem_base, (uint32_t)p.tmem_cols);
   }
 
-  // ===== prologue: LayerNorm(x) -> resident bf16 A tile (all warps) =====
-  {
+  // ===== prologue: LayerNorm(x) -> resident bf16 A tile (warps 1..) =====
+  if (warp > 0) {
     constexpr int UNR = KV == 1 ? 4 : (KV == 2 ? 7 : 2);   // rows in flight per warp (measured: 7 helps at C = 192, hurts at C = 384)
     const float* x = p.x;
     const int M = p.M;
-    build_a_tile<LPR, KV, UNR, true>(a_smem, C, C16, p.ln_w, p.ln_b, p.ln_eps, warp, MLP_WARPS, lane, [&](int r, int k) {
+    build_a_tile<LPR, KV, UNR, true>(a_smem, C, C16, p.ln_w, p.ln_b, p.ln_eps, warp - 1, MLP_WARPS - 1, lane, [&](int r, int k) {
       const long long m = m0 + r;
       if (m >= M) return make_float4(0.f, 0.f, 0.f, 0.f);
       return *reinterpret_cast<const float4*>(x + m * C + k);
     });
   }
   fence_proxy_async();
-  mbar_arrive_warp(&sh->a_ready);
+  tc_fence_before();
+  __syncthreads();     // barrier inits, TMEM base address, staged biases and the A tile are visible to every role
+  tc_fence_after();
+  const uint32_t tmem_base = sh->tmem_base;
   if (warp == 1) MLP_PROF_ADD(12, t_cta0);
 
   if (warp == 0) {
@@ -173,7 +177,6 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(const MlpParams p) 
     }
   } else if (warp == 1) {
     // ===== MMA issuer: warp-uniform loop, one elected lane issues tcgen05.mma / commit =====
-    MLP_TIMED(0, mbar_wait(&sh->a_ready, 0));
     const long long t_mma0 = MLP_CLOCK();
     const uint32_t idesc1 = umma_idesc_bf16(TILE_M, (uint32_t)HC);
     const uint32_t idesc2 = umma_idesc_bf16(TILE_M, (uint32_t)TR);

@@ -62,33 +62,38 @@ __global__ void __launch_bounds__(RG_THREADS, 1) rowgemm_kernel(const RowGemmPar
       mbar_init(&sh->tmem_full[b], 1);
       mbar_init(&sh->tmem_empty[b], epi_count / 32);
     }
-    mbar_init(&sh->a_ready, RG_THREADS / 32);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(&sh->tmem_base, tmem_cols);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = sh->tmem_base;
-
-  // weight prefetch: the first ring fill needs no empty-wait, start it before the prologue
+  // Per-CTA setup runs in warp 0 WHILE warps 1.. build the A tile (this kernel is not persistent: with the setup in
+  // front of the prologue, 26 % of all stall samples of the qkv GEMM sat at the barrier behind tcgen05.alloc,
+  // profiles/r2_ncu_rowgemm_qkv192.txt): first ring fill (same thread as the barrier init: program order), TMEM
+  // allocation, bias -> shared memory (the epilogue's per-block __ldg of the bias was another 14 %).
   const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.Wp);
   const int prefetch = min(p.stages, total_tiles);
-  if (threadIdx.x == 0) {
-    for (int t = 0; t < prefetch; ++t) {
-      mbar_arrive_expect_tx(&sh->full[t], (uint32_t)stage_bytes);
-      bulk_g2s(ring + t * stage_bytes, wsrc + (size_t)t * stage_bytes, (uint32_t)stage_bytes, &sh->full[t]);
+  float* bias_s = reinterpret_cast<float*>(sh + 1);
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int t = 0; t < prefetch; ++t) {
+        mbar_arrive_expect_tx(&sh->full[t], (uint32_t)stage_bytes);
+        bulk_g2s(ring + t * stage_bytes, wsrc + (size_t)t * stage_bytes, (uint32_t)stage_bytes, &sh->full[t]);
+      }
     }
+    __syncwarp();
+    tmem_alloc(&sh->tmem_base, tmem_cols);
+    if (p.bias)
+      for (int i = lane; i < p.nchunks * p.NT; i += 32) bias_s[i] = p.bias[i];
   }
 
-  // ===== prologue: all warps build the resident A tile (bf16, swizzled) =====
-  {
+  // ===== prologue: warps 1.. build the resident A tile (bf16, swizzled) =====
+  if (warp > 0) {
+    const int pw = warp - 1;
+    constexpr int PWARPS = RG_WARPS - 1;
     constexpr int UNR = KV == 1 ? 4 : (KV == 2 ? SWN_RG_UNR2 : (KV == 3 ? 2 : 1));
     const int M = p.M;
     if (p.a_mode == A_BF16) {
       const op_t* A = reinterpret_cast<const op_t*>(p.A);
       const int lda = p.lda;
-      build_a_tile<LPR, KV, UNR, false>(a_smem, p.K, K16, nullptr, nullptr, 0.f, warp, RG_WARPS, lane, [&](int r, int k) {
+      build_a_tile<LPR, KV, UNR, false>(a_smem, p.K, K16, nullptr, nullptr, 0.f, pw, PWARPS, lane, [&](int r, int k) {
         const long long m = m0 + r;
         if (m >= M) return make_float4(0.f, 0.f, 0.f, 0.f);
         const uint2 raw = *reinterpret_cast<const uint2*>(A + m * lda + k);
@@ -97,7 +102,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) rowgemm_kernel(const RowGemmPar
     } else if (p.a_mode == A_MERGE_LN) {
       const float* A = reinterpret_cast<const float*>(p.A);
       const int gH = p.gH, gW = p.gW, gC = p.gC, gWo = p.gWo, hw = p.gHo * p.gWo;
-      build_a_tile<LPR, KV, UNR, true>(a_smem, p.K, K16, p.ln_w, p.ln_b, p.ln_eps, warp, RG_WARPS, lane, [&](int r, int k) {
+      build_a_tile<LPR, KV, UNR, true>(a_smem, p.K, K16, p.ln_w, p.ln_b, p.ln_eps, pw, PWARPS, lane, [&](int r, int k) {
         const long long m = m0 + r;
         if (m >= M) return make_float4(0.f, 0.f, 0.f, 0.f);
         const int bb = (int)(m / hw);
@@ -117,13 +122,16 @@ __global__ void __launch_bounds__(RG_THREADS, 1) rowgemm_kernel(const RowGemmPar
         return *reinterpret_cast<const float4*>(A + m * lda + k);
       };
       if (p.a_mode == A_F32_LN)
-        build_a_tile<LPR, KV, UNR, true>(a_smem, p.K, K16, p.ln_w, p.ln_b, p.ln_eps, warp, RG_WARPS, lane, ld);
+        build_a_tile<LPR, KV, UNR, true>(a_smem, p.K, K16, p.ln_w, p.ln_b, p.ln_eps, pw, PWARPS, lane, ld);
       else
-        build_a_tile<LPR, KV, UNR, false>(a_smem, p.K, K16, nullptr, nullptr, 0.f, warp, RG_WARPS, lane, ld);
+        build_a_tile<LPR, KV, UNR, false>(a_smem, p.K, K16, nullptr, nullptr, 0.f, pw, PWARPS, lane, ld);
     }
   }
   fence_proxy_async();
-  mbar_arrive_warp(&sh->a_ready);
+  tc_fence_before();
+  __syncthreads();     // barrier inits, TMEM base address, bias and the A tile are visible to every role
+  tc_fence_after();
+  const uint32_t tmem_base = sh->tmem_base;
 
   if (warp == 0) {
     // ===== weight producer: remaining tiles, consumption order =====
@@ -137,7 +145,6 @@ __global__ void __launch_bounds__(RG_THREADS, 1) rowgemm_kernel(const RowGemmPar
     }
   } else if (warp == 1) {
     // ===== MMA issuer: warp-uniform loop, one elected lane issues tcgen05.mma / commit =====
-    mbar_wait(&sh->a_ready, 0);
     const uint32_t idesc = umma_idesc_bf16(TILE_M, (uint32_t)p.NT);
     const uint64_t a_desc0 = umma_desc_sw128(smem_u32(a_smem));
     const uint64_t ring_desc0 = umma_desc_sw128(smem_u32(ring));
@@ -243,7 +250,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) rowgemm_kernel(const RowGemmPar
         mbar_wait(&sh->tmem_full[buf], ((uint32_t)n >> 1) & 1u);
         tc_fence_after();
         const uint32_t t_row = lane_addr + (uint32_t)(buf * nt32);
-        const float* bias = p.bias ? p.bias + n * p.NT : nullptr;
+        const float* bias = p.bias ? bias_s + n * p.NT : nullptr;
         const long long col0 = (long long)n * p.n_valid;
         for (int jb = half; jb < nblk; jb += 2) {
           tmem_ld16(t_row + jb * 16, v);
@@ -253,7 +260,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) rowgemm_kernel(const RowGemmPar
           if (bias) {
 #pragma unroll
             for (int j4 = 0; j4 < 16; j4 += 4) {
-              const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + c0 + j4));
+              const float4 bv = *reinterpret_cast<const float4*>(bias + c0 + j4);
               v[j4] += bv.x; v[j4 + 1] += bv.y; v[j4 + 2] += bv.z; v[j4 + 3] += bv.w;
             }
           }
@@ -316,7 +323,7 @@ int launch_rowgemm(RowGemmParams p, cudaStream_t stream) {
   const int KB = (K16 + 63) >> 6;
   const int stage_bytes = p.NT * 128;
   const int a_bytes = KB * A_KBLOCK_BYTES;
-  const int fixed = 1024 + a_bytes + (int)sizeof(RgSmem) + 64;
+  const int fixed = 1024 + a_bytes + (int)sizeof(RgSmem) + 64 + p.nchunks * p.NT * 4;   // + bias staged in shared memory
   // aim for >= 2 co-resident CTAs per SM (smem <= ~113 KB) when that still leaves >= 2 ring stages
   int stages = (113 * 1024 - fixed) / stage_bytes;
   if (stages < 2) stages = (232448 - fixed) / stage_bytes;
