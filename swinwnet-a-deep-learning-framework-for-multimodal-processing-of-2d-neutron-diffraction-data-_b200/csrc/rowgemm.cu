@@ -32,7 +32,9 @@ struct RgSmem {
   uint32_t tmem_base;
 };
 
-template <int LPR, int KV>
+// EP: epilogue variant, compile-time so that each one gets its own register allocation (one kernel with all three paths
+// needed 150 registers and lost the second co-resident CTA): 0 = direct (E_BF16 / E_F32), 1 = E_EXPAND, 2 = transposed E_F32
+template <int LPR, int KV, int EP>
 __global__ void __launch_bounds__(RG_THREADS, 1) rowgemm_kernel(const RowGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -182,7 +184,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) rowgemm_kernel(const RowGemmPar
     const int nblk = p.NT >> 4;
     float v[16];
 
-    if (p.e_mode == E_EXPAND) {
+    if constexpr (EP == 1) {
       // chunk n = channel group (i = n>>1, j = n&1) -> output pixel (2h+i, 2w+j); warps of `half` own the
       // chunks with n & 1 == half, i.e. always TMEM buffer `half`, and a thread sees its whole row (LayerNorm).
       int eb = 0, eh = 0, ew = 0;
@@ -242,6 +244,65 @@ __global__ void __launch_bounds__(RG_THREADS, 1) rowgemm_kernel(const RowGemmPar
         }
         tc_fence_before();
         mbar_arrive_warp(&sh->tmem_empty[half]);
+      }
+    } else if constexpr (EP == 2) {   // launcher chose the transposed epilogue (p.res_stride != 0)
+      // out = alpha * (acc + bias) + residual in TRANSPOSED ownership (common.cuh): after tcgen05.ld a lane holds 16 columns
+      // of its own row, so direct residual loads / stores touch 32 rows x 16 B per instruction and their latency sat in
+      // front of every add (53 % of the stall samples of the C = 384 proj GEMM, profiles/r2_ncu_rowgemm.txt).  The block
+      // goes through 2 KB of per-warp scratch; a lane then owns 16-byte chunk (lane & 3) of rows ps*8 + lane/4, the
+      // residual of the NEXT block (next chunk included) is requested before the current one is consumed — the first one
+      // before the accumulator is even waited for.
+      uint8_t* scr = reinterpret_cast<uint8_t*>(bias_s + ((p.nchunks * p.NT + 3) & ~3)) + (warp - 2) * EPI_SCRATCH_BYTES;
+      const int cq = (lane & 3) * 4, rq = lg * 32 + (lane >> 2);
+      auto load_res = [&](int n, int jb, float4* xr) {
+        const int c = jb * 16 + cq;
+        const bool on = p.res != nullptr && n < p.nchunks && c < p.n_valid;
+#pragma unroll
+        for (int ps = 0; ps < 4; ++ps) {
+          const long long mm = m0 + rq + ps * 8;
+          xr[ps] = (on && mm < p.M) ? __ldg(reinterpret_cast<const float4*>(p.res + mm * p.ldres + (long long)n * p.n_valid + c))
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      float4 xr_cur[4], xr_nxt[4];
+      load_res(0, half, xr_cur);
+      for (int n = 0; n < p.nchunks; ++n) {
+        const int buf = n & 1;
+        mbar_wait(&sh->tmem_full[buf], ((uint32_t)n >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t t_row = lane_addr + (uint32_t)(buf * nt32);
+        const float* bias = p.bias ? bias_s + n * p.NT : nullptr;
+        const long long col0 = (long long)n * p.n_valid;
+        for (int jb = half; jb < nblk; jb += 2) {
+          if (jb + 2 < nblk) load_res(n, jb + 2, xr_nxt); else load_res(n + 1, half, xr_nxt);
+          tmem_ld16(t_row + jb * 16, v);
+          tmem_ld_wait();
+          const int c0 = jb * 16;
+#pragma unroll
+          for (int j4 = 0; j4 < 16; j4 += 4) {
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (bias) bv = *reinterpret_cast<const float4*>(bias + c0 + j4);
+            v[j4] = (v[j4] + bv.x) * alpha; v[j4 + 1] = (v[j4 + 1] + bv.y) * alpha;
+            v[j4 + 2] = (v[j4 + 2] + bv.z) * alpha; v[j4 + 3] = (v[j4 + 3] + bv.w) * alpha;
+          }
+          epi_scatter16(scr, v, lane);
+          const int c = c0 + cq;
+          if (c < p.n_valid) {
+#pragma unroll
+            for (int ps = 0; ps < 4; ++ps) {
+              const long long mm = m0 + rq + ps * 8;
+              if (mm >= p.M) continue;
+              const float4 y = epi_gather4(scr, ps, lane);
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + mm * p.ldo + col0 + c) =
+                  make_float4(y.x + xr_cur[ps].x, y.y + xr_cur[ps].y, y.z + xr_cur[ps].z, y.w + xr_cur[ps].w);
+            }
+          }
+#pragma unroll
+          for (int ps = 0; ps < 4; ++ps) xr_cur[ps] = xr_nxt[ps];
+          __syncwarp();
+        }
+        tc_fence_before();
+        mbar_arrive_warp(&sh->tmem_empty[buf]);
       }
     } else {
       const bool vec8 = (p.ldo % 8 == 0) && (p.n_valid % 8 == 0);
@@ -323,7 +384,12 @@ int launch_rowgemm(RowGemmParams p, cudaStream_t stream) {
   const int KB = (K16 + 63) >> 6;
   const int stage_bytes = p.NT * 128;
   const int a_bytes = KB * A_KBLOCK_BYTES;
-  const int fixed = 1024 + a_bytes + (int)sizeof(RgSmem) + 64 + p.nchunks * p.NT * 4;   // + bias staged in shared memory
+  // The transposed fp32 epilogue (coalesced, prefetched residual) pays for wide outputs with a residual (C = 384 proj:
+  // 0.262 -> 0.176 ms) and loses on narrow ones (48 columns: 0.54 -> 0.82 ms: its 16 KB of scratch costs co-resident CTAs).
+  p.res_stride = (p.e_mode == E_F32 && p.res != nullptr && p.nchunks * p.n_valid >= 128 && p.ldres % 4 == 0) ? 1 : 0;
+  // + bias staged in shared memory, + 2 KB transposition scratch per epilogue warp for the transposed fp32 epilogue
+  const int fixed = 1024 + a_bytes + (int)sizeof(RgSmem) + 64 + p.nchunks * p.NT * 4 + 16 +
+                    (p.res_stride ? (RG_WARPS - 2) * EPI_SCRATCH_BYTES : 0);
   // aim for >= 2 co-resident CTAs per SM (smem <= ~113 KB) when that still leaves >= 2 ring stages
   int stages = (113 * 1024 - fixed) / stage_bytes;
   if (stages < 2) stages = (232448 - fixed) / stage_bytes;
@@ -341,13 +407,17 @@ int launch_rowgemm(RowGemmParams p, cudaStream_t stream) {
     SWN_CUDA(cudaGetLastError());
     return 0;
   };
-  if (p.K <= 16) return go(rowgemm_kernel<4, 1>);
-  if (p.K <= 32) return go(rowgemm_kernel<8, 1>);
-  if (p.K <= 64) return go(rowgemm_kernel<16, 1>);
-  if (p.K <= 128) return go(rowgemm_kernel<32, 1>);
-  if (p.K <= 256) return go(rowgemm_kernel<32, 2>);
-  if (p.K <= 384) return go(rowgemm_kernel<32, 3>);
-  return go(rowgemm_kernel<32, 6>);
+  const int ep = p.e_mode == E_EXPAND ? 1 : (p.res_stride ? 2 : 0);
+#define SWN_RG_DISPATCH(LPR_, KV_) \
+  return ep == 1 ? go(rowgemm_kernel<LPR_, KV_, 1>) : (ep == 2 ? go(rowgemm_kernel<LPR_, KV_, 2>) : go(rowgemm_kernel<LPR_, KV_, 0>))
+  if (p.K <= 16) SWN_RG_DISPATCH(4, 1);
+  if (p.K <= 32) SWN_RG_DISPATCH(8, 1);
+  if (p.K <= 64) SWN_RG_DISPATCH(16, 1);
+  if (p.K <= 128) SWN_RG_DISPATCH(32, 1);
+  if (p.K <= 256) SWN_RG_DISPATCH(32, 2);
+  if (p.K <= 384) SWN_RG_DISPATCH(32, 3);
+  SWN_RG_DISPATCH(32, 6);
+#undef SWN_RG_DISPATCH
 }
 
 }  // namespace swn
