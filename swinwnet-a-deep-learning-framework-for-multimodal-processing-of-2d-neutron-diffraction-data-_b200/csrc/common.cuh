@@ -198,11 +198,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug must surface as a trapped kernel (cudaErrorLaunchFailure), never as
 // a hung GPU.  Every legitimate wait in these kernels is microseconds; the retry budget is seconds.
+#ifndef SWN_MBAR_BACKOFF_NS
+#define SWN_MBAR_BACKOFF_NS 0
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   uint32_t tries = 0;
   while (!mbar_try_wait(bar, parity)) {
+#if SWN_MBAR_BACKOFF_NS > 0
+    __nanosleep(SWN_MBAR_BACKOFF_NS);   // waiting roles must not compete with the working warps for issue slots
+#endif
     if ((++tries & 63u) == 0 && clock64() - t0 > 8000000000LL) {
       printf("swn: mbarrier wait timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
       __trap();

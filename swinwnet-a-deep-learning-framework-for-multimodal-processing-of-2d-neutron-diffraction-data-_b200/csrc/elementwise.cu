@@ -190,11 +190,10 @@ __global__ void __launch_bounds__(128) conv_head_kernel(const float* __restrict_
 // four lanes that share a pixel, cropped NCHW store.  TF32 keeps 10 mantissa bits of the operands (error ~1e-4 of the
 // output scale, 200x inside the 2e-2 gate); the fp32 CUDA-core kernel above stays as the exact variant.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
+// fp32 -> TF32, round-to-nearest (ties away from zero on the magnitude): adding half a TF32 ulp to the bit pattern lets
+// the mma's truncation of the low 13 mantissa bits do the rounding.  One integer add; `cvt.rna.tf32.f32` runs on a
+// slow conversion pipe and was 12 % of the recon head's stall samples (profiles/r2_ncu_heads.txt).
+__device__ __forceinline__ float to_tf32(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
 __device__ __forceinline__ void mma_tf32(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
@@ -233,17 +232,53 @@ __global__ void __launch_bounds__(256) conv_head_mma_kernel(const float* __restr
   if (tid < 8) in_s[(TH + 2) * (TW + 2) * CIP + tid] = 0.f;
   const int tiles_x = (Wout + TW - 1) / TW, tiles_y = (Hout + TH - 1) / TH;
   const long long n_tiles = (long long)B * tiles_y * tiles_x;
+  // halo tile of the input: NLD float4 per thread.  Narrow inputs (CI <= 16: the recon head) are register-prefetched one
+  // tile ahead — the loads of tile i+1 are in flight while tile i runs its mma phase (they were 31 % of the stall samples
+  // when they sat in front of the staging stores); wide inputs load in one batch at the top of the tile.
+  constexpr int NLD = ((TH + 2) * (TW + 2) * (CI / 4) + 255) / 256;
+  constexpr bool PREFETCH = NLD <= 4;
+  float4 pre[PREFETCH ? NLD : 1];
+  auto load_tile = [&](long long tile, float4* dst) {
+    const int b = (int)(tile / (tiles_y * tiles_x));
+    const int tr = (int)(tile - (long long)b * tiles_y * tiles_x);
+    const int y0 = (tr / tiles_x) * TH, x0 = (tr % tiles_x) * TW;
+#pragma unroll
+    for (int q = 0; q < NLD; ++q) {
+      const int i = tid + q * 256;
+      const int c4 = i % (CI / 4), pix = i / (CI / 4);
+      const int yy = y0 - 1 + pix / (TW + 2), xx = x0 - 1 + pix % (TW + 2);
+      dst[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < (TH + 2) * (TW + 2) * (CI / 4) && yy >= 0 && yy < Hh && xx >= 0 && xx < Wh)
+        dst[q] = __ldg(reinterpret_cast<const float4*>(tok + (((long long)b * Hh + yy) * Wh + xx) * CI + c4 * 4));
+    }
+  };
+  auto store_tile = [&](const float4* src) {
+#pragma unroll
+    for (int q = 0; q < NLD; ++q) {
+      const int i = tid + q * 256;
+      if (i < (TH + 2) * (TW + 2) * (CI / 4)) {
+        const int c4 = i % (CI / 4), pix = i / (CI / 4);
+        *reinterpret_cast<float4*>(in_s + pix * CIP + c4 * 4) = make_float4(to_tf32(src[q].x), to_tf32(src[q].y), to_tf32(src[q].z), to_tf32(src[q].w));
+      }
+    }
+  };
+  if constexpr (PREFETCH) if ((long long)blockIdx.x < n_tiles) load_tile(blockIdx.x, pre);
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int b = (int)(tile / (tiles_y * tiles_x));
     const int tr = (int)(tile - (long long)b * tiles_y * tiles_x);
     const int y0 = (tr / tiles_x) * TH, x0 = (tr % tiles_x) * TW;
     __syncthreads();   // previous tile fully consumed (and the weights staged, first time round)
-    for (int i = tid; i < (TH + 2) * (TW + 2) * (CI / 4); i += 256) {
-      const int c4 = i % (CI / 4), pix = i / (CI / 4);
-      const int yy = y0 - 1 + pix / (TW + 2), xx = x0 - 1 + pix % (TW + 2);
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (yy >= 0 && yy < Hh && xx >= 0 && xx < Wh) v = __ldg(reinterpret_cast<const float4*>(tok + (((long long)b * Hh + yy) * Wh + xx) * CI + c4 * 4));
-      *reinterpret_cast<float4*>(in_s + pix * CIP + c4 * 4) = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+    if constexpr (PREFETCH) {
+      store_tile(pre);
+      if (tile + gridDim.x < n_tiles) load_tile(tile + gridDim.x, pre);
+    } else {   // (a 16-float4 register batch was measured slower here: 124 registers)
+      for (int i = tid; i < (TH + 2) * (TW + 2) * (CI / 4); i += 256) {
+        const int c4 = i % (CI / 4), pix = i / (CI / 4);
+        const int yy = y0 - 1 + pix / (TW + 2), xx = x0 - 1 + pix % (TW + 2);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (yy >= 0 && yy < Hh && xx >= 0 && xx < Wh) v = __ldg(reinterpret_cast<const float4*>(tok + (((long long)b * Hh + yy) * Wh + xx) * CI + c4 * 4));
+        *reinterpret_cast<float4*>(in_s + pix * CIP + c4 * 4) = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+      }
     }
     __syncthreads();
     float acc[2][NT][4];
