@@ -236,6 +236,18 @@ __global__ void __launch_bounds__(RP_THREADS, 1) rowgemm_persist_kernel(const Ro
       if (rrs) mbar_wait(&sh->in_full[s], ((uint32_t)it >> 1) & 1u);   // residual rows have landed
       const float* res_row = rrs ? reinterpret_cast<const float*>(rstg + s * TILE_M * rrs + r * rrs)
                                  : (has_res ? p.res + m * p.ldres : nullptr);
+      // residual read from GLOBAL memory (rows too wide to stage): requested one 16-column block ahead, the first block of
+      // a tile before its accumulator is waited for — these loads sat in front of every add (37 % of the stall samples of the
+      // C = 192 proj GEMM, profiles/r2_ncu_lines_n_p192.txt)
+      const bool gres = EM == E_F32 && !rrs && has_res && row_ok;
+      float4 rcur[4], rnxt[4];
+      auto ldres = [&](int n, int jb, float4* dst) {
+        const int c0 = jb * 16, nvb = n < nchunks ? min(16, n_valid - c0) : 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          dst[q] = (gres && q * 4 < nvb) ? __ldg(reinterpret_cast<const float4*>(res_row + n * n_valid + c0 + q * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      ldres(0, half, rcur);
       for (int n = 0; n < nchunks; ++n) {
         mbar_wait(&sh->acc_full[buf], acc_ph);
         tc_fence_after();
@@ -243,10 +255,17 @@ __global__ void __launch_bounds__(RP_THREADS, 1) rowgemm_persist_kernel(const Ro
         const float* bias = bias_s + n * NT;
         const int col0 = n * n_valid;
         for (int jb = half; jb < nblk; jb += 2) {
+          if (jb + 2 < nblk) ldres(n, jb + 2, rnxt); else ldres(n + 1, half, rnxt);
           tmem_ld16(t_row + jb * 16, v);
           tmem_ld_wait();
           const int c0 = jb * 16;
           const int nvb = min(16, n_valid - c0);
+          float4 rr[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            rr[q] = rcur[q];
+            rcur[q] = rnxt[q];
+          }
           if (!row_ok || nvb <= 0) continue;
 #pragma unroll
           for (int j4 = 0; j4 < 16; j4 += 4) {
@@ -271,7 +290,10 @@ __global__ void __launch_bounds__(RP_THREADS, 1) rowgemm_persist_kernel(const Ro
             for (int j4 = 0; j4 < 16; j4 += 4) {
               if (j4 < nvb) {
                 float4 a = make_float4(v[j4] * alpha, v[j4 + 1] * alpha, v[j4 + 2] * alpha, v[j4 + 3] * alpha);
-                if (res_row) {
+                if (gres) {
+                  const float4 rv = rr[j4 >> 2];
+                  a.x += rv.x; a.y += rv.y; a.z += rv.z; a.w += rv.w;
+                } else if (res_row) {
                   const float4 rv = *reinterpret_cast<const float4*>(res_row + col0 + c0 + j4);
                   a.x += rv.x; a.y += rv.y; a.z += rv.z; a.w += rv.w;
                 }
