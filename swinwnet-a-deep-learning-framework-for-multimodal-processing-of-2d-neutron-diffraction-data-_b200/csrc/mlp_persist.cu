@@ -49,13 +49,22 @@ constexpr int MP_EPI_SPLIT = SWN_MP_EPI_SPLIT;  // epilogue warps per TMEM lane 
 constexpr int MP_WARPS = 8 + 4 * MP_EPI_SPLIT;
 constexpr int MP_THREADS = MP_WARPS * 32;
 constexpr int MP_LN_WARPS = 4;
+// Share of the FINAL epilogue (Y + b2 + residual -> out) that the LayerNorm warps take over (staged variant): they are
+// busy ~4.5 k of the ~18 k cycles of a C = 96 tile while the 8 epilogue warps carry GELU (6.5 k) AND the final epilogue
+// (4 k) on the critical path (profiles/r2a_mlp_role_waits.txt).  1 = the LN warps take two thirds of the 16-column blocks.
+// MEASURED SLOWER (C = 96: 0.934 -> 1.077 ms, C = 48: 0.620 -> 0.808 ms, with the Y accumulator double-buffered): the deferred
+// final epilogue holds the staging buffer of tile i until LN(i+1) is done, which delays the row loads of tile i+2 (the staging
+// would need a third buffer).  Off by default.
+#ifndef SWN_MP_FINAL_LN
+#define SWN_MP_FINAL_LN 0
+#endif
 constexpr int MP_EPI_THREADS = 128 * MP_EPI_SPLIT;
 
 struct MpSmem {
   uint64_t full[8], empty[8];
   uint64_t in_full[2], in_empty[2];
   uint64_t hacc_full[2], hacc_empty[2], hs_full[2], hs_empty[2];
-  uint64_t a_full[2], a_empty[2], y_full, y_empty;    // DIRECT: two A tiles (LayerNorm of tile i+1 overlaps the GEMMs of tile i)
+  uint64_t a_full[2], a_empty[2], y_full[2], y_empty[2];    // DIRECT: two A tiles (LayerNorm of tile i+1 overlaps the GEMMs of tile i)
   uint32_t tmem_base;
 };
 
@@ -71,7 +80,9 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
   const int nj = (4 * C) / HC;
   const int nkk = (HC + 63) >> 6, steps2 = HC >> 4;
   const int nT = C16 / TR;
-  const int hbase = (C16 + 31) & ~31;
+  constexpr int NY = DIRECT ? 1 : 2;          // staged variant: two Y accumulators (the final epilogue of tile i overlaps the GEMMs of tile i+1)
+  const int ystride = (C16 + 31) & ~31;
+  const int hbase = NY * ystride;
   const int stage_bytes = max(HC, TR) * 128;
   const int w1_bytes = HC * 128, w2_bytes = TR * 128;
   const int rs = p.row_stride;  // staging row stride in bytes (odd number of 16-byte chunks)
@@ -92,6 +103,9 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntiles = (p.M + TILE_M - 1) / TILE_M;
+  const int nb = C16 >> 4;                                              // 16-column blocks of Y
+  const int nb_ln = (DIRECT || !SWN_MP_FINAL_LN) ? 0 : (2 * nb + 2) / 3;   // ... of which the LayerNorm warps finish [0, nb_ln)
+  const int fin_warps = MP_EPI_THREADS / 32 + (nb_ln > 0 ? MP_LN_WARPS : 0);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -100,7 +114,7 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&sh->in_full[b], 1);
-      mbar_init(&sh->in_empty[b], MP_EPI_THREADS / 32);
+      mbar_init(&sh->in_empty[b], fin_warps);
       mbar_init(&sh->hacc_full[b], 1);
       mbar_init(&sh->hacc_empty[b], MP_EPI_THREADS / 32);
       mbar_init(&sh->hs_full[b], MP_EPI_THREADS / 32);
@@ -110,8 +124,10 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
       mbar_init(&sh->a_full[b], LN_WARPS);
       mbar_init(&sh->a_empty[b], 1);
     }
-    mbar_init(&sh->y_full, 1);
-    mbar_init(&sh->y_empty, MP_EPI_THREADS / 32);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&sh->y_full[b], 1);
+      mbar_init(&sh->y_empty[b], fin_warps);
+    }
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < 4 * C; i += MP_THREADS) b1s[i] = p.b1[i];
@@ -125,6 +141,39 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = sh->tmem_base;
+
+  // final epilogue of the staged variant for the 32 rows of lane group `lg`, 16-column blocks cb0, cb0 + step, ... < cb1:
+  // out = Y + b2 + residual is formed in place in the staging row (row-per-lane, conflict free), then stored in the transposed
+  // ownership (common.cuh): 8 rows x 64 contiguous bytes per warp instruction
+  auto final_blocks = [&](int tile, int s, int lg, int cb0, int step, int cb1) {
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)((NY == 2 ? s : 0) * ystride);   // Y buffer = tile parity = s
+    uint8_t* stile = stg + s * TILE_M * rs;
+    uint8_t* res = stile + (lg * 32 + lane) * rs;
+    float v[16];
+    for (int cb = cb0; cb < cb1; cb += step) {
+      tmem_ld16(lane_addr + (uint32_t)(cb * 16), v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j4 = 0; j4 < 16; j4 += 4) {
+        const int c = cb * 16 + j4;
+        if (c < C) {
+          const float4 xr = *reinterpret_cast<const float4*>(res + c * 4);
+          const float4 bb = *reinterpret_cast<const float4*>(b2s + c);
+          *reinterpret_cast<float4*>(res + c * 4) = make_float4(v[j4 + 0] + bb.x + xr.x, v[j4 + 1] + bb.y + xr.y, v[j4 + 2] + bb.z + xr.z, v[j4 + 3] + bb.w + xr.w);
+        }
+      }
+      __syncwarp();
+      const int c = cb * 16 + (lane & 3) * 4;
+      if (c < C) {
+#pragma unroll
+        for (int ps = 0; ps < 4; ++ps) {
+          const int rl = lg * 32 + ps * 8 + (lane >> 2);
+          const long long mm = (long long)tile * TILE_M + rl;
+          if (mm < p.M) *reinterpret_cast<float4*>(p.out + mm * C + c) = *reinterpret_cast<const float4*>(stile + rl * rs + c * 4);
+        }
+      }
+    }
+  };
 
   if (warp == 0) {
     // ===== weight producer: the whole fc1/fc2 stream once per tile =====
@@ -176,6 +225,8 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int g0 = it * nj;  // global chunk counter of this tile's first chunk
       const int ab = NA == 2 ? (it & 1) : 0;                       // A buffer of this tile
+      const int yb = NY == 2 ? (it & 1) : 0;                       // Y accumulator of this tile
+      const uint32_t yph = NY == 2 ? (((uint32_t)it >> 1) & 1u) : ((uint32_t)it & 1u);
       const uint32_t aph = NA == 2 ? (((uint32_t)it >> 1) & 1u) : ((uint32_t)it & 1u);
       auto gemm1 = [&](int j) {
         const int g = g0 + j, buf = g & 1;
@@ -203,7 +254,7 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
       auto gemm2 = [&](int j) {
         const int g = g0 + j, buf = g & 1;
         MP_TIMED(3, mbar_wait(&sh->hs_full[buf], ((uint32_t)g >> 1) & 1u));
-        if (j == 0) MP_TIMED(5, mbar_wait(&sh->y_empty, ((uint32_t)it & 1u) ^ 1u));  // previous tile's Y drained
+        if (j == 0) MP_TIMED(5, mbar_wait(&sh->y_empty[yb], yph ^ 1u));  // the tile that used this Y accumulator is drained
         const uint64_t hd0 = hs_desc0 + (uint64_t)(buf * nkk * kblk_d16);
         for (int kk = 0; kk < nkk; ++kk) {
           const int steps = min(4, steps2 - kk * 4);
@@ -214,11 +265,11 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
               const uint64_t ad = hd0 + (uint64_t)(kk * kblk_d16), bd = ring_desc0 + (uint64_t)(rp.s * stage_d16);
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                if (k < steps) umma_bf16(tmem_base + (uint32_t)(tt * TR), ad + 2 * k, bd + 2 * k, idesc2, (j | kk | k) != 0 ? 1u : 0u);
+                if (k < steps) umma_bf16(tmem_base + (uint32_t)(yb * ystride + tt * TR), ad + 2 * k, bd + 2 * k, idesc2, (j | kk | k) != 0 ? 1u : 0u);
               umma_commit(&sh->empty[rp.s]);
               if (kk == nkk - 1 && tt == nT - 1) {
                 umma_commit(&sh->hs_empty[buf]);
-                if (j == nj - 1) umma_commit(&sh->y_full);
+                if (j == nj - 1) umma_commit(&sh->y_full[yb]);
               }
             }
             __syncwarp();
@@ -309,6 +360,25 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
 #if SWN_MLP_PROFILE
       if (p.phase_cycles && warp == 4 && lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.phase_cycles + 14), (unsigned long long)(clock64() - t_ln0));
 #endif
+      // this warp's share of the PREVIOUS tile's final epilogue (its accumulator completes while this tile's chunks start)
+      if (nb_ln > 0 && it > 0) {
+        const int jt = it - 1;
+        mbar_wait(&sh->y_full[jt & 1], ((uint32_t)jt >> 1) & 1u);
+        tc_fence_after();
+        final_blocks(tile - (int)gridDim.x, jt & 1, warp & 3, 0, 1, nb_ln);
+        tc_fence_before();
+        mbar_arrive_warp(&sh->y_empty[jt & 1]);
+        mbar_arrive_warp(&sh->in_empty[jt & 1]);
+      }
+    }
+    if (!DIRECT && nb_ln > 0 && it > 0) {   // the last tile of this CTA
+      const int jt = it - 1;
+      mbar_wait(&sh->y_full[jt & 1], ((uint32_t)jt >> 1) & 1u);
+      tc_fence_after();
+      final_blocks(blockIdx.x + jt * (int)gridDim.x, jt & 1, warp & 3, 0, 1, nb_ln);
+      tc_fence_before();
+      mbar_arrive_warp(&sh->y_empty[jt & 1]);
+      mbar_arrive_warp(&sh->in_empty[jt & 1]);
     }
   } else if (warp >= 8) {
     // ===== epilogue warps 8..: MP_EPI_SPLIT warps per TMEM lane group split the 16-column blocks =====
@@ -375,7 +445,9 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
 #endif
       }
       // final: Y + b2 + residual(staging) -> out
-      if (warp == 8) MP_TIMED(9, mbar_wait(&sh->y_full, (uint32_t)it & 1u)); else mbar_wait(&sh->y_full, (uint32_t)it & 1u);
+      const int yb = NY == 2 ? (it & 1) : 0;
+      const uint32_t yph = NY == 2 ? (((uint32_t)it >> 1) & 1u) : ((uint32_t)it & 1u);
+      if (warp == 8) MP_TIMED(9, mbar_wait(&sh->y_full[yb], yph)); else mbar_wait(&sh->y_full[yb], yph);
       tc_fence_after();
       const long long t_f0 = SWN_MLP_PROFILE ? clock64() : 0;
       if (DIRECT) {
@@ -421,39 +493,13 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
           __syncwarp();
         }
       } else {
-      // out = Y + b2 + residual is formed in place in the staging row (row-per-lane, conflict free), then stored in the
-      // transposed ownership (common.cuh): 8 rows x 64 contiguous bytes per warp instruction
-      uint8_t* stile = stg + s * TILE_M * rs;
-      uint8_t* res = stile + r * rs;
-      for (int cb = part; cb < (C16 >> 4); cb += MP_EPI_SPLIT) {
-        tmem_ld16(lane_addr + (uint32_t)(cb * 16), v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j4 = 0; j4 < 16; j4 += 4) {
-          const int c = cb * 16 + j4;
-          if (c < C) {
-            const float4 xr = *reinterpret_cast<const float4*>(res + c * 4);
-            *reinterpret_cast<float4*>(res + c * 4) =
-                make_float4(v[j4 + 0] + b2s[c + 0] + xr.x, v[j4 + 1] + b2s[c + 1] + xr.y, v[j4 + 2] + b2s[c + 2] + xr.z, v[j4 + 3] + b2s[c + 3] + xr.w);
-          }
-        }
-        __syncwarp();
-        const int c = cb * 16 + (lane & 3) * 4;
-        if (c < C) {
-#pragma unroll
-          for (int ps = 0; ps < 4; ++ps) {
-            const int rl = lg * 32 + ps * 8 + (lane >> 2);
-            const long long mm = (long long)tile * TILE_M + rl;
-            if (mm < p.M) *reinterpret_cast<float4*>(p.out + mm * C + c) = *reinterpret_cast<const float4*>(stile + rl * rs + c * 4);
-          }
-        }
-      }
+      final_blocks(tile, s, lg, nb_ln + part, MP_EPI_SPLIT, nb);
       }
 #if SWN_MLP_PROFILE
       if (p.phase_cycles && warp == 8 && lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.phase_cycles + 10), (unsigned long long)(clock64() - t_f0));
 #endif
       tc_fence_before();
-      mbar_arrive_warp(&sh->y_empty);
+      mbar_arrive_warp(&sh->y_empty[yb]);
       if (!DIRECT) mbar_arrive_warp(&sh->in_empty[s]);
     }
   }
@@ -471,7 +517,7 @@ int launch_mlp_persist(MlpParams p, int num_sms, cudaStream_t stream) {
   const bool direct = C > 96;    // rows too wide to stage twice: LayerNorm warps read global memory directly
   const int nj = (4 * C) / p.HC;
   const int KB1 = (C16 + 63) >> 6, nkk = (p.HC + 63) >> 6;
-  int cols = ((C16 + 31) & ~31) + (nj > 1 ? 2 : 1) * p.HC, tc = 32;
+  int cols = (direct ? 1 : 2) * ((C16 + 31) & ~31) + (nj > 1 ? 2 : 1) * p.HC, tc = 32;
   while (tc < cols) tc <<= 1;
   SWN_CHECK(tc <= 512, "mlp_persist: TMEM overflow");
   {
