@@ -136,13 +136,16 @@ __device__ __forceinline__ void fb_attention_pair(const uint8_t* u_s, uint8_t* a
     m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
     m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
     m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-#pragma unroll
-    for (int ks = 0; ks < 2; ++ks) {
-      pa[mt][ks][0] = fb_exp2_pack(s[mt][2 * ks][0], s[mt][2 * ks][1], m0);
-      pa[mt][ks][1] = fb_exp2_pack(s[mt][2 * ks][2], s[mt][2 * ks][3], m1);
-      pa[mt][ks][2] = fb_exp2_pack(s[mt][2 * ks + 1][0], s[mt][2 * ks + 1][1], m0);
-      pa[mt][ks][3] = fb_exp2_pack(s[mt][2 * ks + 1][2], s[mt][2 * ks + 1][3], m1);
-    }
+    pa[mt][0][0] = fb_exp2_pack(s[mt][0][0], s[mt][0][1], m0);
+    pa[mt][0][1] = fb_exp2_pack(s[mt][0][2], s[mt][0][3], m1);
+    pa[mt][0][2] = fb_exp2_pack(s[mt][1][0], s[mt][1][1], m0);
+    pa[mt][0][3] = fb_exp2_pack(s[mt][1][2], s[mt][1][3], m1);
+    pa[mt][1][0] = fb_exp2_pack(s[mt][2][0], s[mt][2][1], m0);
+    pa[mt][1][1] = fb_exp2_pack(s[mt][2][2], s[mt][2][3], m1);
+    // key columns 24..31 (n-tile 3): the odd ones (25, 27, 29, 31) are padding for EVERY lane (bias image -1e30 -> P = 0):
+    // no exponential is issued for them (the attention core is MUFU-bound: 12.5 % fewer ex2 per pair)
+    pa[mt][1][2] = pack_op(ex2_approx(s[mt][3][0] - m0), 0.f);
+    pa[mt][1][3] = pack_op(ex2_approx(s[mt][3][2] - m1), 0.f);
   }
   // O = P V  (+ one extra 8-column tile of ones: its accumulator is the softmax denominator of the row)
   const int vcol0 = voff & ~7;
