@@ -338,9 +338,183 @@ __global__ void __launch_bounds__(256) conv_head_mma_kernel(const float* __restr
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// fp16-operand variant of the head kernel (default): same implicit GEMM on mma.sync.m16n8k16 with fp32 accumulation.  fp16 has
+// the mantissa of TF32 (10 bits), so the rounding error of the operands is the same as in the TF32 kernel above, but one mma
+// covers 16 input channels instead of 8 (half the mma and fragment-load instructions: the heads are issue-bound) and the
+// staged halo tile is half the size.  Inputs are saturated to the fp16 range by the conversion (pack_half2_sat).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack_half2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ void mma_f16(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int CI, int CM>
+__global__ void __launch_bounds__(256) conv_head_h_kernel(const float* __restrict__ tok, const float* __restrict__ w1,
+                                                          const float* __restrict__ b1, const float* __restrict__ w2,
+                                                          const float* __restrict__ b2, float* __restrict__ out, int B,
+                                                          int Hh, int Wh, int Cout, int Hout, int Wout) {
+  constexpr int TH = 8, TW = 32;
+  constexpr int KST = (CI + 15) / 16;                     // k16 steps per tap
+  constexpr int K16 = KST * 16;
+  constexpr int PSB = ((K16 * 2 / 16) % 2 == 1) ? K16 * 2 : K16 * 2 + 16;   // pixel stride in bytes: odd number of 16-byte chunks
+  constexpr int NT = (CM + 7) / 8;                        // n8 tiles
+  constexpr int WSB = 48;                                 // weight row (one n, 16 k) stride in bytes: conflict-free B loads
+  static_assert(CI % 4 == 0 && CM % 2 == 0, "unsupported head shape");
+  extern __shared__ __align__(16) uint8_t ch_s[];
+  uint8_t* w_s = ch_s;                                    // [9][KST][NT*8][WSB]
+  uint8_t* in_s = w_s + 9 * KST * NT * 8 * WSB;           // [(TH+2)*(TW+2)][PSB]
+  float* b1_s = reinterpret_cast<float*>(in_s + (TH + 2) * (TW + 2) * PSB);   // [NT*8]
+  float* w2_s = b1_s + NT * 8;                            // [2][NT*8]
+  float* b2_s = w2_s + 2 * NT * 8;                        // [2]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+  for (int i = tid; i < 9 * KST * NT * 8 * 8; i += 256) {          // one half2 (k pair) per step
+    const int kp = i % 8, n = (i / 8) % (NT * 8), ks = (i / (8 * NT * 8)) % KST, tap = i / (8 * NT * 8 * KST);
+    const int ci = ks * 16 + kp * 2;
+    const float lo = (n < CM && ci < CI) ? w1[(n * CI + ci) * 9 + tap] : 0.f;
+    const float hi = (n < CM && ci + 1 < CI) ? w1[(n * CI + ci + 1) * 9 + tap] : 0.f;
+    *reinterpret_cast<uint32_t*>(w_s + ((tap * KST + ks) * NT * 8 + n) * WSB + kp * 4) = pack_half2_sat(lo, hi);
+  }
+  for (int i = tid; i < NT * 8; i += 256) {
+    b1_s[i] = i < CM ? b1[i] : 0.f;
+    w2_s[i] = i < CM ? w2[i] : 0.f;
+    w2_s[NT * 8 + i] = (i < CM && Cout > 1) ? w2[CM + i] : 0.f;
+  }
+  if (tid < 2) b2_s[tid] = tid < Cout ? b2[tid] : 0.f;
+  // zero the k padding of every pixel once (channels CI..K16 are never written by the staging loop)
+  if (K16 > CI)
+    for (int i = tid; i < (TH + 2) * (TW + 2); i += 256)
+      for (int c = CI; c < K16; c += 2) *reinterpret_cast<uint32_t*>(in_s + i * PSB + c * 2) = 0u;
+  const int tiles_x = (Wout + TW - 1) / TW, tiles_y = (Hout + TH - 1) / TH;
+  const long long n_tiles = (long long)B * tiles_y * tiles_x;
+  constexpr int NLD = ((TH + 2) * (TW + 2) * (CI / 4) + 255) / 256;
+  constexpr bool PREFETCH = NLD <= 4;
+  float4 pre[PREFETCH ? NLD : 1];
+  auto load_tile = [&](long long tile, float4* dst) {
+    const int b = (int)(tile / (tiles_y * tiles_x));
+    const int tr = (int)(tile - (long long)b * tiles_y * tiles_x);
+    const int y0 = (tr / tiles_x) * TH, x0 = (tr % tiles_x) * TW;
+#pragma unroll
+    for (int q = 0; q < NLD; ++q) {
+      const int i = tid + q * 256;
+      const int c4 = i % (CI / 4), pix = i / (CI / 4);
+      const int yy = y0 - 1 + pix / (TW + 2), xx = x0 - 1 + pix % (TW + 2);
+      dst[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < (TH + 2) * (TW + 2) * (CI / 4) && yy >= 0 && yy < Hh && xx >= 0 && xx < Wh)
+        dst[q] = __ldg(reinterpret_cast<const float4*>(tok + (((long long)b * Hh + yy) * Wh + xx) * CI + c4 * 4));
+    }
+  };
+  if constexpr (PREFETCH) if ((long long)blockIdx.x < n_tiles) load_tile(blockIdx.x, pre);
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int b = (int)(tile / (tiles_y * tiles_x));
+    const int tr = (int)(tile - (long long)b * tiles_y * tiles_x);
+    const int y0 = (tr / tiles_x) * TH, x0 = (tr % tiles_x) * TW;
+    __syncthreads();   // previous tile fully consumed (and the weights staged, first time round)
+    if constexpr (PREFETCH) {
+#pragma unroll
+      for (int q = 0; q < NLD; ++q) {
+        const int i = tid + q * 256;
+        if (i < (TH + 2) * (TW + 2) * (CI / 4)) {
+          const int c4 = i % (CI / 4), pix = i / (CI / 4);
+          *reinterpret_cast<uint2*>(in_s + pix * PSB + c4 * 8) = make_uint2(pack_half2_sat(pre[q].x, pre[q].y), pack_half2_sat(pre[q].z, pre[q].w));
+        }
+      }
+      if (tile + gridDim.x < n_tiles) load_tile(tile + gridDim.x, pre);
+    } else {
+      for (int i = tid; i < (TH + 2) * (TW + 2) * (CI / 4); i += 256) {
+        const int c4 = i % (CI / 4), pix = i / (CI / 4);
+        const int yy = y0 - 1 + pix / (TW + 2), xx = x0 - 1 + pix % (TW + 2);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (yy >= 0 && yy < Hh && xx >= 0 && xx < Wh) v = __ldg(reinterpret_cast<const float4*>(tok + (((long long)b * Hh + yy) * Wh + xx) * CI + c4 * 4));
+        *reinterpret_cast<uint2*>(in_s + pix * PSB + c4 * 8) = make_uint2(pack_half2_sat(v.x, v.y), pack_half2_sat(v.z, v.w));
+      }
+    }
+    __syncthreads();
+    float acc[2][NT][4];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int n = 0; n < NT; ++n) acc[m][n][0] = acc[m][n][1] = acc[m][n][2] = acc[m][n][3] = 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      // A rows = 16 consecutive pixels of image row (warp + tap/3) starting at x offset tap%3 (+16 for the second m tile)
+      const uint8_t* arow = in_s + ((warp + tap / 3) * (TW + 2) + tap % 3 + g) * PSB + t4 * 4;
+      const uint8_t* wt = w_s + (tap * KST * NT * 8 + g) * WSB + t4 * 4;
+#pragma unroll
+      for (int ks = 0; ks < KST; ++ks) {
+        uint32_t a[2][4];
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          const uint8_t* ap = arow + m * 16 * PSB + ks * 32;
+          a[m][0] = *reinterpret_cast<const uint32_t*>(ap);
+          a[m][1] = *reinterpret_cast<const uint32_t*>(ap + 8 * PSB);
+          a[m][2] = *reinterpret_cast<const uint32_t*>(ap + 16);
+          a[m][3] = *reinterpret_cast<const uint32_t*>(ap + 8 * PSB + 16);
+        }
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+          const uint8_t* wp = wt + (ks * NT * 8 + n * 8) * WSB;
+          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wp), b1v = *reinterpret_cast<const uint32_t*>(wp + 16);
+          mma_f16(acc[0][n], a[0], b0, b1v);
+          mma_f16(acc[1][n], a[1], b0, b1v);
+        }
+      }
+    }
+    // epilogue: accumulator (row g | g+8 = pixel, col 2*t4 | 2*t4+1 = channel)
+    const int y = y0 + warp;
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      float o[2][2] = {{0.f, 0.f}, {0.f, 0.f}};   // [pixel half][cout]
+#pragma unroll
+      for (int n = 0; n < NT; ++n)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int ch = n * 8 + 2 * t4 + (e & 1);
+          const float h = gelu_erf(acc[m][n][e] + b1_s[ch]);
+          o[e >> 1][0] = fmaf(h, w2_s[ch], o[e >> 1][0]);
+          o[e >> 1][1] = fmaf(h, w2_s[NT * 8 + ch], o[e >> 1][1]);
+        }
+#pragma unroll
+      for (int hlf = 0; hlf < 2; ++hlf)
+#pragma unroll
+        for (int co = 0; co < 2; ++co) {
+          float r = o[hlf][co];
+          r += __shfl_xor_sync(0xffffffffu, r, 1);
+          r += __shfl_xor_sync(0xffffffffu, r, 2);
+          const int x = x0 + m * 16 + hlf * 8 + g;
+          if (t4 == 0 && co < Cout && y < Hout && x < Wout) out[(((long long)b * Cout + co) * Hout + y) * Wout + x] = r + b2_s[co];
+        }
+    }
+  }
+}
+
+#ifndef SWN_HEAD_F16
+#define SWN_HEAD_F16 1
+#endif
+
 template <int CI, int CM>
 static int launch_conv_head_mma(const float* tok, const float* w1, const float* b1, const float* w2, const float* b2, float* out,
                                 int B, int Hh, int Wh, int Cout, int Hout, int Wout, int ctas_per_sm, cudaStream_t st) {
+  const long long n_tiles_h = (long long)B * ((Hout + 7) / 8) * ((Wout + 31) / 32);
+  if (SWN_HEAD_F16) {
+    constexpr int KSTH = (CI + 15) / 16, K16 = KSTH * 16, NTH = (CM + 7) / 8;
+    constexpr int PSB = ((K16 * 2 / 16) % 2 == 1) ? K16 * 2 : K16 * 2 + 16;
+    const size_t smem_h = (size_t)9 * KSTH * NTH * 8 * 48 + (size_t)10 * 34 * PSB + (size_t)(NTH * 8 * 3 + 2) * sizeof(float) + 16;
+    SWN_CUDA(cudaFuncSetAttribute(conv_head_h_kernel<CI, CM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
+    int dev_h = 0, sms_h = 148;
+    if (cudaGetDevice(&dev_h) == cudaSuccess) cudaDeviceGetAttribute(&sms_h, cudaDevAttrMultiProcessorCount, dev_h);
+    long long grid_h = (long long)sms_h * ctas_per_sm;
+    if (grid_h > n_tiles_h) grid_h = n_tiles_h;
+    conv_head_h_kernel<CI, CM><<<(unsigned)grid_h, 256, smem_h, st>>>(tok, w1, b1, w2, b2, out, B, Hh, Wh, Cout, Hout, Wout);
+    SWN_CUDA(cudaGetLastError());
+    return 0;
+  }
   constexpr int CIP = (CI % 32 == 16) ? CI + 4 : CI, KST = (CI + 7) / 8, NT = (CM + 7) / 8;
   const size_t smem = (size_t)(9 * KST * 8 * 24 + 10 * 34 * CIP + 8 + NT * 8 * 3 + 2) * sizeof(float);
   SWN_CUDA(cudaFuncSetAttribute(conv_head_mma_kernel<CI, CM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
