@@ -30,6 +30,10 @@ struct RgSmem {
   uint64_t tmem_empty[2];
   uint64_t a_ready;
   uint32_t tmem_base;
+  // A_MERGE_LN: per-row source of the 2x2 gather, computed once per row (the index divisions were 47 % of the executed
+  // instructions of the merge GEMM when every float4 load redid them, profiles/r2_ncu_lines_n_mg48.txt)
+  long long row_off[TILE_M];   // element offset of pixel (2ho, 2wo) of the row's image
+  int row_flag[TILE_M];        // bit 0: row < M, bit 1: 2ho+1 < gH, bit 2: 2wo+1 < gW
 };
 
 // EP: epilogue variant, compile-time so that each one gets its own register allocation (one kernel with all three paths
@@ -104,16 +108,30 @@ __global__ void __launch_bounds__(RG_THREADS, 1) rowgemm_kernel(const RowGemmPar
     } else if (p.a_mode == A_MERGE_LN) {
       const float* A = reinterpret_cast<const float*>(p.A);
       const int gH = p.gH, gW = p.gW, gC = p.gC, gWo = p.gWo, hw = p.gHo * p.gWo;
+      {
+        const int rr = (int)threadIdx.x - 32;       // prologue threads 32..159 <-> rows 0..127
+        if (rr < TILE_M) {
+          const long long m = m0 + rr;
+          int flag = 0;
+          long long off = 0;
+          if (m < M) {
+            const int bb = (int)(m / hw);
+            const int rem = (int)(m - (long long)bb * hw);
+            const int ho = rem / gWo, wo = rem - ho * gWo;
+            off = (((long long)bb * gH + 2 * ho) * gW + 2 * wo) * gC;
+            flag = 1 | (2 * ho + 1 < gH ? 2 : 0) | (2 * wo + 1 < gW ? 4 : 0);
+          }
+          sh->row_off[rr] = off;
+          sh->row_flag[rr] = flag;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"((RG_WARPS - 1) * 32) : "memory");   // prologue warps only (warp 0 runs the setup)
+      }
+      const long long dyoff = (long long)gW * gC;
       build_a_tile<LPR, KV, UNR, true>(a_smem, p.K, K16, p.ln_w, p.ln_b, p.ln_eps, pw, PWARPS, lane, [&](int r, int k) {
-        const long long m = m0 + r;
-        if (m >= M) return make_float4(0.f, 0.f, 0.f, 0.f);
-        const int bb = (int)(m / hw);
-        const int rem = (int)(m - (long long)bb * hw);
-        const int ho = rem / gWo, wo = rem - ho * gWo;
-        const int q = k / gC, ch = k - q * gC;
-        const int y = 2 * ho + (q & 1), x = 2 * wo + (q >> 1);
-        if (y >= gH || x >= gW) return make_float4(0.f, 0.f, 0.f, 0.f);
-        return *reinterpret_cast<const float4*>(A + (((long long)bb * gH + y) * gW + x) * gC + ch);
+        const int q = (k >= gC) + (k >= 2 * gC) + (k >= 3 * gC), ch = k - q * gC;     // [x00, x10, x01, x11]: dy = q & 1, dx = q >> 1
+        const int flag = sh->row_flag[r];
+        if (!(flag & 1) || ((q & 1) && !(flag & 2)) || ((q >> 1) && !(flag & 4))) return make_float4(0.f, 0.f, 0.f, 0.f);
+        return *reinterpret_cast<const float4*>(A + sh->row_off[r] + (q & 1) * dyoff + (q >> 1) * gC + ch);
       });
     } else {
       const float* A = reinterpret_cast<const float*>(p.A);
@@ -202,6 +220,9 @@ __global__ void __launch_bounds__(RG_THREADS, 1) rowgemm_kernel(const RowGemmPar
         const uint32_t t_row = lane_addr + (uint32_t)(half * nt32);
         const int oy = 2 * eh + (n >> 1), ox = 2 * ew + (n & 1);
         const bool act = row_ok && oy < p.xHs && ox < p.xWs;
+        float* orow = reinterpret_cast<float*>(p.out) + (((long long)eb * p.xHs + oy) * p.xWs + ox) * (long long)p.ldo;
+        // (keeping the chunk row in registers for ONE TMEM round trip instead of three was measured slower: 127 registers
+        // cost the co-resident CTAs these latency-bound shapes live on: expand C=48 0.475 -> 0.757 ms)
         float s = 0.f;
         for (int jb = 0; jb < nblk; ++jb) {
           tmem_ld16(t_row + jb * 16, v);
@@ -221,7 +242,6 @@ __global__ void __launch_bounds__(RG_THREADS, 1) rowgemm_kernel(const RowGemmPar
           }
         }
         const float rstd = rsqrtf(q * inv_n + p.ln_eps);
-        float* orow = reinterpret_cast<float*>(p.out) + (((long long)eb * p.xHs + oy) * p.xWs + ox) * (long long)p.ldo;
         for (int jb = 0; jb < nblk; ++jb) {
           tmem_ld16(t_row + jb * 16, v);
           tmem_ld_wait();

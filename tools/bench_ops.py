@@ -110,5 +110,25 @@ for (L, C, nH, H, W) in SHAPES:
         ms = timeit(lambda: ops.rowgemm(A=att, a_mode=ops.A_BF16, M=M, K=C, lda=C, Wp=Wp, NT=NT, nchunks=nch, n_valid=nv,
                                         e_mode=ops.E_F32, bias=bp, out=out, ldo=C, res=x, ldres=C))
         report("proj", M, C, ms, M * C * 10, 2.0 * M * C * C)
+    if "merge" in a.ops and C <= 192:
+        pm = S.model.PatchMerging(C).to(DEV)
+        xm = x.view(B, L, C)
+        with torch.no_grad():
+            ms = timeit(lambda: pm(xm, (H, W)))
+        Mo = B * ((H + 1) // 2) * ((W + 1) // 2)
+        report("merge", M, C, ms, M * C * 4 + Mo * 2 * C * 4, 2.0 * Mo * 4 * C * 2 * C)
+    if "expand" in a.ops and C >= 24:
+        pe = S.model.PatchExpanding(C).to(DEV)
+        xe = x.view(B, L, C)
+        with torch.no_grad():
+            ms = timeit(lambda: pe.run(xe, (H, W)))
+        report("expand", M, C, ms, M * C * 4 + M * 4 * (C // 2) * 4, 2.0 * M * C * 2 * C)
+    if "declin" in a.ops and C >= 96:
+        Wl, bl = torch.randn(C // 2, C, device=DEV) * C ** -0.5, torch.zeros(C // 2, device=DEV)
+        Wp, bp, NT, nch = packing.pack_rowgemm(Wl, bl, packing.choose_chunk(C // 2, 256))
+        o = torch.empty(M, C // 2, device=DEV)
+        ms = timeit(lambda: ops.rowgemm(A=x, a_mode=ops.A_F32, M=M, K=C, lda=C, Wp=Wp, NT=NT, nchunks=nch, n_valid=packing.choose_chunk(C // 2, 256),
+                                        e_mode=ops.E_F32, bias=bp, out=o, ldo=C // 2))
+        report("declin", M, C, ms, M * C * 6, 2.0 * M * C * (C // 2))
     del x
     torch.cuda.empty_cache()
