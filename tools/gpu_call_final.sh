@@ -1,0 +1,14 @@
+#!/bin/bash
+# round-end evidence: full GPU suite, bench line, ncu pass over one bench step (launch list + DRAM traffic per family)
+set -u
+cd "$(dirname "$0")/.."
+O=gpurun_out
+mkdir -p $O
+timeout 1800 python -m pytest tests -m gpu -q -p no:cacheprovider > $O/final_tests.log 2>&1
+echo "tests rc=$?"; tail -5 $O/final_tests.log
+timeout 900 python bench.py > $O/final_bench.json 2> $O/final_bench.err
+echo "bench rc=$?"; tail -2 $O/final_bench.err
+timeout 600 python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-library-bar --no-parity-check > $O/final_plain.log 2>&1 && \
+timeout 1500 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:swn -s 660 -c 222 --csv --log-file $O/final_step.csv \
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-library-bar --no-parity-check > $O/final_ncu.log 2>&1
+echo "ncu rc=$?"; tail -2 $O/final_ncu.log
