@@ -223,24 +223,23 @@ __global__ void __launch_bounds__(RG_THREADS, 1) rowgemm_kernel(const RowGemmPar
         float* orow = reinterpret_cast<float*>(p.out) + (((long long)eb * p.xHs + oy) * p.xWs + ox) * (long long)p.ldo;
         // (keeping the chunk row in registers for ONE TMEM round trip instead of three was measured slower: 127 registers
         // cost the co-resident CTAs these latency-bound shapes live on: expand C=48 0.475 -> 0.757 ms)
-        float s = 0.f;
+        // LayerNorm statistics in ONE pass over the accumulator (shifted moments, shift = first channel: no cancellation
+        // for |mean| >> std), second pass normalises and stores: two TMEM round trips per chunk row instead of three
+        float s1 = 0.f, s2 = 0.f, v0 = 0.f;
         for (int jb = 0; jb < nblk; ++jb) {
           tmem_ld16(t_row + jb * 16, v);
           tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) s += (jb * 16 + j < p.n_valid) ? v[j] : 0.f;
-        }
-        const float mean = s * inv_n;
-        float q = 0.f;
-        for (int jb = 0; jb < nblk; ++jb) {
-          tmem_ld16(t_row + jb * 16, v);
-          tmem_ld_wait();
+          if (jb == 0) v0 = v[0];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float d = v[j] - mean;
-            q += (jb * 16 + j < p.n_valid) ? d * d : 0.f;
+            const float d = (jb * 16 + j < p.n_valid) ? v[j] - v0 : 0.f;
+            s1 += d;
+            s2 = fmaf(d, d, s2);
           }
         }
+        const float m1 = s1 * inv_n;
+        const float mean = v0 + m1;
+        const float q = fmaxf(s2 - s1 * m1, 0.f);
         const float rstd = rsqrtf(q * inv_n + p.ln_eps);
         for (int jb = 0; jb < nblk; ++jb) {
           tmem_ld16(t_row + jb * 16, v);
