@@ -103,6 +103,18 @@ struct FusedBlockParams {   // fused W-MSA (+ MLP) block, shift 0, resident pack
 };
 int launch_swin_fused(FusedBlockParams p, int num_sms, cudaStream_t stream);
 
+// ---- swin_warp.cu ---------------------------------------------------------------------------
+struct WarpBlockParams {    // whole block, shift 0, C in {12, 24}: one warp per window (packing.py::pack_warp_block)
+  const float* x;     // [B, H*W, C] fp32
+  float* out;         // [B, H*W, C] fp32 (must not alias x)
+  int B, H, W, C, nH;
+  float eps;
+  const op_t* Wpk;    // weight fragments: q | k | v^T | proj | fc1 | fc2
+  const float* fpk;   // b2 [K16] | relative-position bias fragments [nH][2][4][32][4]
+  int nWy, nWx, n_windows;   // filled in by the launcher
+};
+int launch_swin_warp_block(WarpBlockParams p, int num_sms, cudaStream_t stream);
+
 // ---- cross_attn.cu --------------------------------------------------------------------------
 struct CrossAttnParams {
   const op_t* q;   // [B, Lq, C]

@@ -24,6 +24,8 @@ leaf operator goes through ``autograd.KernelOp``: the forward is the same kernel
 the operator with its fp32 torch restatement (``torch_ref.py``) on the saved inputs.  Under ``torch.no_grad()`` nothing of
 that is touched (in-place ping-pong buffers, no saved tensors).
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -33,6 +35,9 @@ WINDOW = 5
 FUSED_BLOCK = True   # route shift-0 blocks of the widths below through the single-kernel paths (csrc/swin_fused.cu)
 FUSED_WHOLE = {(12, 3), (24, 3), (48, 3), (48, 6)}    # (C, heads) instances of swin_fused_kernel (whole block)
 FUSED_ATTN = {(96, 3), (96, 6)}                       # instances of swin_attn_stream_kernel (attention half)
+# (C, heads) that run one warp per window on mma.sync register fragments (csrc/swin_warp.cu) instead of swin_fused_kernel;
+# SWN_WARP_BLOCK=0 keeps the tcgen05 block kernel for A/B measurements
+WARP_BLOCK = {(12, 3), (24, 3)} if os.environ.get("SWN_WARP_BLOCK", "1") != "0" else set()
 
 
 def _check_infer(x):
@@ -131,6 +136,7 @@ class SwinTransformerBlock(nn.Module):
         self.mlp = nn.Sequential(nn.Linear(dim, hidden), nn.GELU(), nn.Dropout(drop), nn.Linear(hidden, dim), nn.Dropout(drop))
         self._cache = _PackCache()
         self._cache_fused = _PackCache()
+        self._cache_warp = _PackCache()
         if drop or attn_drop or drop_path:
             raise NotImplementedError("swinwnet_b200: dropout/drop_path > 0 is a training feature (not implemented)")
 
@@ -174,6 +180,20 @@ class SwinTransformerBlock(nn.Module):
             return packing.pack_fused_block(*src, self.num_heads)
         return self._cache_fused.get(src, build)
 
+    def _packed_warp(self):
+        a = self.attn
+        src = [self.norm1.weight, self.norm1.bias, a.qkv.weight, a.qkv.bias, a.relative_position_bias_table,
+               a.proj.weight, a.proj.bias, self.norm2.weight, self.norm2.bias, self.mlp[0].weight, self.mlp[0].bias,
+               self.mlp[3].weight, self.mlp[3].bias]
+
+        def build():
+            if a.qkv.bias is None:
+                raise NotImplementedError("swinwnet_b200: qkv_bias=False is not supported")
+            if self.window_size != WINDOW or int(self.dim * self.mlp_ratio) != 4 * self.dim:
+                raise NotImplementedError("swinwnet_b200: kernels are built for window_size=5, mlp_ratio=4")
+            return packing.pack_warp_block(*src, self.num_heads)
+        return self._cache_warp.get(src, build)
+
     def _packed_attn_stream(self):
         a = self.attn
         src = [self.norm1.weight, self.norm1.bias, a.qkv.weight, a.qkv.bias, a.relative_position_bias_table,
@@ -188,7 +208,12 @@ class SwinTransformerBlock(nn.Module):
         H, W = resolution
         assert L == H * W, "input feature has wrong size"
         if FUSED_BLOCK and (C, self.num_heads) in FUSED_WHOLE and self.shift_size == 0 and x.data_ptr() != out.data_ptr():
-            # narrow layers (C = 12 / 24 / 48): the whole block is one tcgen05 kernel (csrc/swin_fused.cu)
+            if (C, self.num_heads) in WARP_BLOCK:
+                # C = 12 / 24: one warp per window, everything in mma.sync register fragments (csrc/swin_warp.cu)
+                Wpk, fpk = self._packed_warp()
+                ops.swin_block_warp(x, out, B, H, W, C, self.num_heads, self.norm1.eps, Wpk, fpk)
+                return out
+            # narrow layers (C = 48, and 12 / 24 when opted out above): the whole block is one tcgen05 kernel (csrc/swin_fused.cu)
             Wpk, fpk = self._packed_fused()
             ops.swin_block_fused(x, out, B, H, W, C, self.num_heads, self.norm1.eps, Wpk, fpk, True)
             return out

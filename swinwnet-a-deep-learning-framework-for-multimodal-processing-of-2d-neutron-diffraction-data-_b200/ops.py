@@ -16,7 +16,7 @@ def operand_dtype():
 
 
 LAUNCH_COUNT = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
-_LAUNCHES_PER_CALL = {"swin_block_small": 1, "swin_block_fused": 1, "rowgemm": 1,"mlp": 1, "window_attention": 1, "cross_attention": 1, "patch_embed": 1,
+_LAUNCHES_PER_CALL = {"swin_block_small": 1, "swin_block_fused": 1, "swin_block_warp": 1, "rowgemm": 1,"mlp": 1, "window_attention": 1, "cross_attention": 1, "patch_embed": 1,
                       "seg_head": 2, "recon_head": 1, "copy_cols": 1, "sigmoid_mask": 1, "sigmoid_mask_mm": 2,
                       "normalize": 1, "dspace_histogram": 2, "adamw_multi": 1, "ensure_2ch": 1, "grad_bucket_copy": 1}
 
@@ -109,6 +109,15 @@ def swin_block_fused(x, out, B, H, W, C, nH, eps, Wpk, fpk, do_mlp=True):
         _lib.check(_lib.load().swn_swin_block_fused(_ptr(x), _ptr(out), B, H, W, C, nH, eps, _ptr(Wpk), _ptr(fpk),
                                                     int(do_mlp), st), "swn_swin_block_fused")
     _count("swin_block_fused")
+
+
+def swin_block_warp(x, out, B, H, W, C, nH, eps, Wpk, fpk):
+    """whole shift-0 Swin block for C = 12 / 24 (3 heads): one warp per window on mma.sync register fragments
+    (csrc/swin_warp.cu); out must not alias x."""
+    with _Launch(x, out, Wpk, fpk) as st:
+        _lib.check(_lib.load().swn_swin_block_warp(_ptr(x), _ptr(out), B, H, W, C, nH, eps, _ptr(Wpk), _ptr(fpk), st),
+                   "swn_swin_block_warp")
+    _count("swin_block_warp")
 
 
 def set_phase_profile(buf):

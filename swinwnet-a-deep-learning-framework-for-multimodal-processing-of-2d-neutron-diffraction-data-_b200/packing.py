@@ -177,6 +177,85 @@ def pack_fused_block(n1w, n1b, Wqkv, bqkv, table, Wproj, bproj, n2w, n2b, W1, b1
     return Wpk, fpk
 
 
+def warp_block_geometry(C: int):
+    """(K16, KT, NJ) of csrc/swin_warp.cu::WbGeom: padded row width, its 16-column k-steps, 8-column tiles with real channels"""
+    K16 = ceil_to(C, 16)
+    return K16, K16 // 16, ceil_to(C, 8) // 8
+
+
+def mma_b_fragments(Wm: torch.Tensor) -> torch.Tensor:
+    """Wm [N, K] (row n = output column, N % 8 == 0, K % 16 == 0) -> [K/16, N/8, 32, 4]: the B operand of
+    mma.sync.m16n8k16 for k-step kt / column tile nt, per lane the pairs (k, k+1) and (k+8, k+9) with
+    k = 16 kt + 2 (lane % 4), n = 8 nt + lane // 4."""
+    N, K = Wm.shape
+    dev = Wm.device
+    kt, nt, lane, e = torch.meshgrid(torch.arange(K // 16, device=dev), torch.arange(N // 8, device=dev),
+                                     torch.arange(32, device=dev), torch.arange(4, device=dev), indexing="ij")
+    return Wm[nt * 8 + lane // 4, kt * 16 + (lane % 4) * 2 + e % 2 + (e // 2) * 8].contiguous()
+
+
+def mma_a_fragments(Wm: torch.Tensor) -> torch.Tensor:
+    """Wm [M, K] (M, K % 16 == 0) -> [M/16, K/16, 32, 8]: the A operand of mma.sync.m16n8k16, per lane the registers
+    a0..a3 = (row g, k), (row g+8, k), (row g, k+8), (row g+8, k+8) with g = lane // 4, k = 16 kt + 2 (lane % 4), two
+    consecutive k each."""
+    M, K = Wm.shape
+    dev = Wm.device
+    mt, kt, lane, e = torch.meshgrid(torch.arange(M // 16, device=dev), torch.arange(K // 16, device=dev),
+                                     torch.arange(32, device=dev), torch.arange(8, device=dev), indexing="ij")
+    r = e // 2
+    return Wm[mt * 16 + lane // 4 + (r % 2) * 8, kt * 16 + (lane % 4) * 2 + (r // 2) * 8 + e % 2].contiguous()
+
+
+def pack_warp_block(n1w, n1b, Wqkv, bqkv, table, Wproj, bproj, n2w, n2b, W1, b1, W2, b2, num_heads: int):
+    """Parameters of one SwinTransformerBlock (nn.Module layouts) -> (Wpk 16-bit flat, fpk fp32 flat) for
+    csrc/swin_warp.cu (C = 12 / 24, 3 heads).
+
+    Wpk = mma.sync fragments of [Wq | Wk | Wv (as A operand: v is produced transposed) | Wproj | W1 | W2], every matrix
+    zero-padded to whole 8 / 16 tiles.  Folds done here in fp32: LayerNorm gamma into the columns of the following
+    weight; biases as two extra k columns — column C multiplies a constant 1 (the plain bias), column C+1 multiplies 1
+    for real tokens and 0 for zero-padded window tokens (W beta: the padded tokens of the reference are zeros AFTER
+    norm1, SwinWNet.py:242,254); head_dim^-0.5 log2(e) into q, log2(e) into the relative-position bias.
+    fpk = [b2 (K16) | bias fragments (nH * 1024)]."""
+    C = Wqkv.shape[1]
+    if num_heads != 3 or C not in (12, 24):
+        raise ValueError(f"pack_warp_block: C={C}, num_heads={num_heads} not supported (12 / 24 channels, 3 heads)")
+    K16, KT, NJ = warp_block_geometry(C)
+    dev = Wqkv.device
+    LOG2E = 1.4426950408889634
+    qs = (C // num_heads) ** -0.5 * LOG2E
+    f = lambda t: t.detach().float()
+
+    def aug(Wm, b, gamma, beta, rows, split_beta):
+        z = torch.zeros(rows, K16, device=dev)
+        n = Wm.shape[0]
+        z[:n, :C] = Wm if gamma is None else Wm * gamma[None, :]
+        z[:n, C] = b
+        if beta is not None:
+            if split_beta:
+                z[:n, C + 1] = Wm @ beta
+            else:
+                z[:n, C] += Wm @ beta
+        return z
+
+    g1, be1, g2, be2 = f(n1w), f(n1b), f(n2w), f(n2b)
+    Wq, Wk, Wv = f(Wqkv)[:C] * qs, f(Wqkv)[C:2 * C], f(Wqkv)[2 * C:]
+    bq, bk, bv = f(bqkv)[:C] * qs, f(bqkv)[C:2 * C], f(bqkv)[2 * C:]
+    W2p = torch.zeros(NJ * 8, 4 * C, device=dev)
+    W2p[:C] = f(W2)
+    parts = [mma_b_fragments(aug(Wq, bq, g1, be1, NJ * 8, True)), mma_b_fragments(aug(Wk, bk, g1, be1, NJ * 8, True)),
+             mma_a_fragments(aug(Wv, bv, g1, be1, K16, True)), mma_b_fragments(aug(f(Wproj), f(bproj), None, None, NJ * 8, False)),
+             mma_b_fragments(aug(f(W1), f(b1), g2, be2, 4 * C, False)), mma_b_fragments(W2p)]
+    Wpk = torch.cat([t.reshape(-1) for t in parts])
+    dt = OPERAND_DTYPE()
+    if dt == torch.float16:
+        Wpk = Wpk.clamp(-65504.0, 65504.0)
+    Wpk = Wpk.to(dt).contiguous()
+    b2p = torch.zeros(K16, device=dev)
+    b2p[:C] = f(b2)
+    fpk = torch.cat([b2p, rel_pos_bias_fragments(f(table), LOG2E).reshape(-1)]).contiguous()
+    return Wpk, fpk
+
+
 def pack_fused_attn_stream(n1w, n1b, Wqkv, bqkv, table, Wproj, bproj, num_heads: int):
     """C = 96 attention half for csrc/swin_fused.cu::swin_attn_stream_kernel: the same folds as pack_fused_block (norm1
     affine, q scale * log2 e, ones block at column 288, bias fragment images), with two differences:

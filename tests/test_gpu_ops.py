@@ -313,6 +313,30 @@ def test_swin_block_fused(C, nH, B, H, W, do_mlp):
     assert relerr(out, ref) <= TOL_BF16 / 4
 
 
+@pytest.mark.parametrize("C,B,H,W", [
+    (12, 2, 10, 15), (12, 2, 13, 9), (12, 1, 40, 65), (12, 1, 5, 5), (12, 1, 3, 4), (12, 1, 240, 245), (12, 3, 100, 190),
+    (24, 2, 10, 15), (24, 1, 32, 61), (24, 1, 5, 5), (24, 1, 2, 7), (24, 1, 180, 175), (24, 2, 125, 240)])
+def test_swin_block_warp(C, B, H, W):
+    """one-warp-per-window block kernel (csrc/swin_warp.cu) against the oracle block: window padding (H, W not multiples
+    of 5: zero tokens AFTER norm1 that still act as keys), images smaller than a window, many windows per warp"""
+    nH = 3
+    x = rnd(B, H * W, C, seed=1) * 1.5 + 0.2
+    sd, order = _block_sd(C, nH)
+    ref = O.swin_block(sd, "", x, (H, W), nH, 0)
+    d = {k: v.to(DEV) for k, v in sd.items()}
+    Wpk, fpk = packing.pack_warp_block(*[d[k] for k in order], nH)
+    xd = x.to(DEV)
+    out = torch.full_like(xd, float("nan"))
+    ops.swin_block_warp(xd, out, B, H, W, C, nH, 1e-5, Wpk, fpk)
+    torch.cuda.synchronize()
+    assert relerr(out, ref) <= TOL_BF16 / 4
+    out2 = torch.full_like(xd, float("nan"))
+    ops.swin_block_warp(xd, out2, B, H, W, C, nH, 1e-5, Wpk, fpk)
+    assert torch.equal(out, out2)                                   # deterministic
+    with pytest.raises(RuntimeError, match="alias"):
+        ops.swin_block_warp(xd, xd, B, H, W, C, nH, 1e-5, Wpk, fpk)
+
+
 @pytest.mark.parametrize("nH,B,H,W", [(3, 2, 10, 15), (6, 1, 13, 9), (3, 1, 63, 120), (6, 2, 100, 101)])
 def test_swin_attn_stream_c96(nH, B, H, W):
     """streamed-weight C=96 attention-half kernel: x + proj(W-MSA(LN1 x)) against the oracle (padding, ragged last
