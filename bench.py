@@ -172,7 +172,7 @@ def library_bar(dev, batches=(8, 64), iters=3):
 # kernel-family accounting: every C-ABI op is bracketed by CUDA events; algorithmic FLOPs / bytes per call
 # =====================================================================================================================
 FAMILIES = {
-    "fused": "swn::swin_fused_kernel + swin_attn_stream_kernel (fused LN1+qkv+W-MSA+proj[+LN2+MLP], C<=96)",
+    "fused": "swn::swin_warp_block_kernel + swin_fused_kernel + swin_attn_stream_kernel (fused LN1+qkv+W-MSA+proj[+LN2+MLP], C<=96)",
     "mlp": "swn::mlp_kernel + mlp_persist_kernel (fused LN2+fc1+GELU+fc2+residual, C>=96)",
     "rowgemm": "swn::rowgemm_kernel + rowgemm_persist_kernel (LN/merge/convert prologue + GEMM + bias/residual/expand epilogue)",
     "window_attn": "swn::window_attn_kernel (W-MSA core on materialised qkv, C>=192)",
@@ -180,7 +180,7 @@ FAMILIES = {
     "heads": "swn::patch_embed_kernel + conv_head_mma_kernel + bilinear_up_kernel",
     "glue": "swn::copy_cols / sigmoid_mask / normalize / ensure_2ch kernels",
 }
-OP_FAMILY = {"swin_block_fused": "fused", "swin_block_small": "fused", "mlp": "mlp", "rowgemm": "rowgemm",
+OP_FAMILY = {"swin_block_fused": "fused", "swin_block_warp": "fused", "swin_block_small": "fused", "mlp": "mlp", "rowgemm": "rowgemm",
              "window_attention": "window_attn", "cross_attention": "cross_attn", "patch_embed": "heads", "seg_head": "heads",
              "recon_head": "heads", "copy_cols": "glue", "sigmoid_mask": "glue", "normalize": "glue", "ensure_2ch": "glue"}
 
@@ -192,7 +192,7 @@ def op_work(name, a, k):
         do_mlp = a[10] if len(a) > 10 else k.get("do_mlp", True)
         M = Bn * Hn * Wn
         return ((24.0 if do_mlp else 8.0) * C * C + 100.0 * C) * M, 8.0 * M * C
-    if name == "swin_block_small":
+    if name in ("swin_block_small", "swin_block_warp"):
         x, out, Bn, Hn, Wn, C = a[:6]
         M = Bn * Hn * Wn
         return (24.0 * C * C + 100.0 * C) * M, 8.0 * M * C

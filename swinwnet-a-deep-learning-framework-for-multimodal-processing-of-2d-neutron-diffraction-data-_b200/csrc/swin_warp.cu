@@ -43,6 +43,36 @@ __device__ __forceinline__ void wb_mma8(float* c, uint32_t a0, uint32_t a1, uint
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a0), "r"(a1), "r"(b0));
 }
+#ifndef SWN_WB_EXP16
+#define SWN_WB_EXP16 0       // 1: softmax exponentials as ex2.approx.f16x2 of the max-subtracted pair (measured slower: 2.49 -> 2.60 ms)
+#endif
+#ifndef SWN_WB_PREFETCH
+#define SWN_WB_PREFETCH 0    // 1: rows of the warp's next window are loaded before the current one is computed (16 / 24 more
+                             // registers: spills at 4 CTAs per SM, and at 3 the gain is lost to the lower occupancy)
+#endif
+// 2^a, 2^b (a, b <= 0: row maximum already subtracted in fp32) as a packed 16-bit pair — the A fragment of P v
+__device__ __forceinline__ uint32_t wb_exp2_pair(float a, float b) {
+#if SWN_WB_EXP16 && !SWN_OPERAND_BF16
+  uint32_t r;
+  const uint32_t x = pack_op(a, b);    // saturating: the -1e30 of masked key columns becomes -65504 -> 2^x = 0
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(r) : "r"(x));
+  return r;
+#else
+  return pack_op(ex2_approx(a), ex2_approx(b));
+#endif
+}
+__device__ __forceinline__ uint32_t wb_exp2_single(float a) {   // (2^a, 0): the odd key columns 25..31 are padding
+#if SWN_WB_EXP16 && !SWN_OPERAND_BF16
+  return wb_exp2_pair(a, -65504.f);
+#else
+  return pack_op(ex2_approx(a), 0.f);
+#endif
+}
+__device__ __forceinline__ float wb_rsqrt(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float quad_sum(float v) {
   v += __shfl_xor_sync(0xffffffffu, v, 1);
   return v + __shfl_xor_sync(0xffffffffu, v, 2);
@@ -132,7 +162,7 @@ __global__ void __launch_bounds__(WB_THREADS, MINB) swin_warp_block_kernel(const
         q = fmaf(d[j][0], d[j][0], q);
         q = fmaf(d[j][1], d[j][1], q);
       }
-      float rstd = rsqrtf(quad_sum(q) * inv_c + p.eps);
+      float rstd = wb_rsqrt(quad_sum(q) * inv_c + p.eps);
       if (first && !real[s]) rstd = 0.f;
       uint32_t pk[NT8];
 #pragma unroll
@@ -145,26 +175,59 @@ __global__ void __launch_bounds__(WB_THREADS, MINB) swin_warp_block_kernel(const
 
   const int nWin2 = p.nWy * p.nWx;
   const int nwarps = gridDim.x * (WB_THREADS / 32);
-  for (int win = blockIdx.x * (WB_THREADS / 32) + warp; win < p.n_windows; win += nwarps) {
+  // token index of the four row slots of window `win` (-1: zero padding of the window / of the second mma tile)
+  auto locate = [&](int win, int (&tok)[4]) {
     const int b = win / nWin2, wr = win - b * nWin2;
     const int wy = wr / p.nWx, wx = wr - wy * p.nWx;
-    // ---- rows of the window: accumulator-fragment layout (row slot, 8-column tile, column pair 2t) ----
-    float x[2][NJ][4];
-    long long tok[4];
-    bool real[4];
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
       const int Y = wy * 5 + dy[s], X = wx * 5 + dx[s];
-      real[s] = Y < p.H && X < p.W;
-      tok[s] = real[s] ? ((long long)b * p.H + Y) * p.W + X : -1;
+      tok[s] = (Y < p.H && X < p.W) ? (b * p.H + Y) * p.W + X : -1;
+    }
+  };
+  // rows in the accumulator-fragment layout (row slot, 8-column tile, column pair 2t)
+  auto load_rows = [&](const int (&tok)[4], float (&v)[2][NJ][4]) {
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
-        float2 v = make_float2(0.f, 0.f);
-        if (real[s] && colv[j]) v = __ldg(reinterpret_cast<const float2*>(p.x + tok[s] * C + 8 * j + 2 * t));
-        x[s >> 1][j][(s & 1) * 2] = v.x;
-        x[s >> 1][j][(s & 1) * 2 + 1] = v.y;
+        float2 r = make_float2(0.f, 0.f);
+        if (tok[s] >= 0 && colv[j]) r = __ldg(reinterpret_cast<const float2*>(p.x + (long long)tok[s] * C + 8 * j + 2 * t));
+        v[s >> 1][j][(s & 1) * 2] = r.x;
+        v[s >> 1][j][(s & 1) * 2 + 1] = r.y;
       }
+  };
+  int win = blockIdx.x * (WB_THREADS / 32) + warp;
+  if (win >= p.n_windows) return;
+#if SWN_WB_PREFETCH
+  int tok_n[4];
+  float x_n[2][NJ][4];
+  locate(win, tok_n);
+  load_rows(tok_n, x_n);
+#endif
+  for (; win < p.n_windows; win += nwarps) {
+    float x[2][NJ][4];
+    int tok[4];
+    bool real[4];
+#if SWN_WB_PREFETCH
+#pragma unroll
+    for (int s = 0; s < 4; ++s) tok[s] = tok_n[s];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int j = 0; j < NJ; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) x[mt][j][e] = x_n[mt][j][e];
+    if (win + nwarps < p.n_windows) {
+      locate(win + nwarps, tok_n);
+      load_rows(tok_n, x_n);
     }
+#else
+    locate(win, tok);
+    load_rows(tok, x);
+#endif
+#pragma unroll
+    for (int s = 0; s < 4; ++s) real[s] = tok[s] >= 0;
     uint32_t a1[2][KT][4];
     layer_norm(x, a1, real, true);
 
@@ -240,14 +303,14 @@ __global__ void __launch_bounds__(WB_THREADS, MINB) swin_warp_block_kernel(const
           m1 = fmaxf(m1, fmaxf(fmaxf(sc[mt][2][2], sc[mt][2][3]), sc[mt][3][2]));
           m0 = quad_max(m0);
           m1 = quad_max(m1);
-          pa[mt][0][0] = pack_op(ex2_approx(sc[mt][0][0] - m0), ex2_approx(sc[mt][0][1] - m0));
-          pa[mt][0][1] = pack_op(ex2_approx(sc[mt][0][2] - m1), ex2_approx(sc[mt][0][3] - m1));
-          pa[mt][0][2] = pack_op(ex2_approx(sc[mt][1][0] - m0), ex2_approx(sc[mt][1][1] - m0));
-          pa[mt][0][3] = pack_op(ex2_approx(sc[mt][1][2] - m1), ex2_approx(sc[mt][1][3] - m1));
-          pa[mt][1][0] = pack_op(ex2_approx(sc[mt][2][0] - m0), ex2_approx(sc[mt][2][1] - m0));
-          pa[mt][1][1] = pack_op(ex2_approx(sc[mt][2][2] - m1), ex2_approx(sc[mt][2][3] - m1));
-          pa[mt][1][2] = pack_op(ex2_approx(sc[mt][3][0] - m0), 0.f);
-          pa[mt][1][3] = pack_op(ex2_approx(sc[mt][3][2] - m1), 0.f);
+          pa[mt][0][0] = wb_exp2_pair(sc[mt][0][0] - m0, sc[mt][0][1] - m0);
+          pa[mt][0][1] = wb_exp2_pair(sc[mt][0][2] - m1, sc[mt][0][3] - m1);
+          pa[mt][0][2] = wb_exp2_pair(sc[mt][1][0] - m0, sc[mt][1][1] - m0);
+          pa[mt][0][3] = wb_exp2_pair(sc[mt][1][2] - m1, sc[mt][1][3] - m1);
+          pa[mt][1][0] = wb_exp2_pair(sc[mt][2][0] - m0, sc[mt][2][1] - m0);
+          pa[mt][1][1] = wb_exp2_pair(sc[mt][2][2] - m1, sc[mt][2][3] - m1);
+          pa[mt][1][2] = wb_exp2_single(sc[mt][3][0] - m0);
+          pa[mt][1][3] = wb_exp2_single(sc[mt][3][2] - m1);
         }
         // O = P v_h and the row sums (P times a tile of ones), both on the tensor cores
         const int mv = (h * G::HD) >> 4, half = ((h * G::HD) >> 3) & 1;
@@ -355,7 +418,7 @@ __global__ void __launch_bounds__(WB_THREADS, MINB) swin_warp_block_kernel(const
 #pragma unroll
         for (int j = 0; j < NJ; ++j)
           if (colv[j])
-            *reinterpret_cast<float2*>(p.out + tok[s] * C + 8 * j + 2 * t) =
+            *reinterpret_cast<float2*>(p.out + (long long)tok[s] * C + 8 * j + 2 * t) =
                 make_float2(x[s >> 1][j][(s & 1) * 2], x[s >> 1][j][(s & 1) * 2 + 1]);
       }
   }
