@@ -195,7 +195,8 @@ def op_work(name, a, k):
     if name in ("swin_block_small", "swin_block_warp"):
         x, out, Bn, Hn, Wn, C = a[:6]
         M = Bn * Hn * Wn
-        return (24.0 * C * C + 100.0 * C) * M, 8.0 * M * C
+        depth = (a[10] if len(a) > 10 else k.get("depth", 1)) if name == "swin_block_warp" else 1   # blocks per launch
+        return depth * (24.0 * C * C + 100.0 * C) * M, 8.0 * M * C
     if name == "mlp":
         M, C = a[2], a[3]
         return 16.0 * M * C * C, 8.0 * M * C

@@ -80,12 +80,13 @@ int swn_swin_block_small(const float* x, float* out, int B, int H, int W, int C,
 int swn_swin_block_fused(const float* x, float* out, int B, int H, int W, int C, int num_heads, float eps,
                          const void* Wpk, const float* fpk, int do_mlp, void* stream);
 
-/* One whole SwinTransformerBlock with shift_size 0 (SwinWNet.py:236-280) for C = 12 / 24 with 3 heads (the
- * UpscalingHead layers at 500x960 / 250x480 tokens, SwinWNet.py:656-678): one warp per 5x5 window, every intermediate in
- * mma.sync register fragments, no block-level synchronisation.  Wpk / fpk = weight fragments and fp32 vectors, see
- * packing.py::pack_warp_block.  out must not alias x. */
+/* `depth` (1..4) consecutive SwinTransformerBlocks with shift_size 0 (SwinWNet.py:236-280; a whole BasicLayer,
+ * SwinWNet.py:320-345, whose blocks all share one window partition) for C = 12 / 24 with 3 heads (the UpscalingHead layers
+ * at 500x960 / 250x480 tokens, SwinWNet.py:656-678): one warp per 5x5 window, every intermediate — including the rows
+ * between the blocks — in mma.sync register fragments, no block-level synchronisation.  Wpk / fpk = the blocks' weight
+ * fragments and fp32 vectors back to back, see packing.py::pack_warp_block.  out must not alias x. */
 int swn_swin_block_warp(const float* x, float* out, int B, int H, int W, int C, int num_heads, float eps, const void* Wpk,
-                        const float* fpk, void* stream);
+                        const float* fpk, int depth, void* stream);
 
 /* Profiling aid: when set to a device buffer of [grid][16] int64 (zeroed by the caller), the fused block kernels add the
  * clock64 cycles thread 0 of each CTA spends in each barrier-delimited phase.  NULL (default) disables it. */

@@ -42,7 +42,7 @@ SIGNATURES = {
     "swn_swin_block_fused": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
                                      c_int, c_void_p]),
     "swn_swin_block_warp": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
-                                    c_void_p]),
+                                    c_int, c_void_p]),
     "swn_set_phase_profile": (c_int, [c_void_p]),
     "swn_window_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                      c_void_p]),

@@ -147,12 +147,12 @@ int swn_swin_block_fused(const float* x, float* out, int B, int H, int W, int C,
 }
 
 int swn_swin_block_warp(const float* x, float* out, int B, int H, int W, int C, int num_heads, float eps, const void* Wpk,
-                        const float* fpk, void* stream) {
+                        const float* fpk, int depth, void* stream) {
   SWN_CHECK(x && out && Wpk && fpk, "swin_block_warp: null pointer");
   SWN_CHECK(x != out, "swin_block_warp: out must not alias x");
   WarpBlockParams p{};
   p.x = x; p.out = out; p.B = B; p.H = H; p.W = W; p.C = C; p.nH = num_heads; p.eps = eps;
-  p.Wpk = reinterpret_cast<const op_t*>(Wpk); p.fpk = fpk;
+  p.Wpk = reinterpret_cast<const op_t*>(Wpk); p.fpk = fpk; p.depth = depth;
   return launch_swin_warp_block(p, num_sms(), reinterpret_cast<cudaStream_t>(stream));
 }
 

@@ -109,8 +109,9 @@ struct WarpBlockParams {    // whole block, shift 0, C in {12, 24}: one warp per
   float* out;         // [B, H*W, C] fp32 (must not alias x)
   int B, H, W, C, nH;
   float eps;
-  const op_t* Wpk;    // weight fragments: q | k | v^T | proj | fc1 | fc2
-  const float* fpk;   // b2 [K16] | relative-position bias fragments [nH][2][4][32][4]
+  const op_t* Wpk;    // per block: weight fragments q | k | v^T | proj | fc1 | fc2       (depth blocks back to back)
+  const float* fpk;   // per block: b2 [K16] | relative-position bias fragments [nH][2][4][32][4]
+  int depth;          // consecutive blocks (same window partition: shift 0) applied to the rows in one pass
   int nWy, nWx, n_windows;   // filled in by the launcher
 };
 int launch_swin_warp_block(WarpBlockParams p, int num_sms, cudaStream_t stream);

@@ -114,21 +114,14 @@ __global__ void __launch_bounds__(WB_THREADS, MINB) swin_warp_block_kernel(const
   constexpr int NJ = G::NJ, NT8 = G::NT8, KT = G::KT;
   extern __shared__ __align__(16) uint8_t wb_smem[];
   uint32_t* w_s = reinterpret_cast<uint32_t*>(wb_smem);
-  float* f_s = reinterpret_cast<float*>(wb_smem + G::W_ELEMS * 2);
-  for (int i = threadIdx.x; i < G::W_ELEMS / 8; i += WB_THREADS)
+  float* f_s = reinterpret_cast<float*>(wb_smem + p.depth * G::W_ELEMS * 2);
+  for (int i = threadIdx.x; i < p.depth * (G::W_ELEMS / 8); i += WB_THREADS)
     reinterpret_cast<uint4*>(w_s)[i] = __ldg(reinterpret_cast<const uint4*>(p.Wpk) + i);
-  for (int i = threadIdx.x; i < G::F_ELEMS / 4; i += WB_THREADS)
+  for (int i = threadIdx.x; i < p.depth * (G::F_ELEMS / 4); i += WB_THREADS)
     reinterpret_cast<float4*>(f_s)[i] = __ldg(reinterpret_cast<const float4*>(p.fpk) + i);
   __syncthreads();
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-  const uint2* wq = reinterpret_cast<const uint2*>(w_s + G::OFF_Q / 2) + lane;
-  const uint2* wk = reinterpret_cast<const uint2*>(w_s + G::OFF_K / 2) + lane;
-  const uint4* wv = reinterpret_cast<const uint4*>(w_s + G::OFF_V / 2) + lane;
-  const uint2* wp = reinterpret_cast<const uint2*>(w_s + G::OFF_P / 2) + lane;
-  const uint2* w1 = reinterpret_cast<const uint2*>(w_s + G::OFF_1 / 2) + lane;
-  const uint2* w2 = reinterpret_cast<const uint2*>(w_s + G::OFF_2 / 2) + lane;
-  const float4* biasfrag = reinterpret_cast<const float4*>(f_s + G::F_BIAS) + lane;
   const uint32_t ONE_ZERO = pack_op(1.f, 0.f), ONE_ONE = pack_op(1.f, 1.f);
 
   // row slot s = 0..3 of this lane: token i = 8 s + g of the window (i >= 25: padding of the second mma tile)
@@ -228,6 +221,18 @@ __global__ void __launch_bounds__(WB_THREADS, MINB) swin_warp_block_kernel(const
 #endif
 #pragma unroll
     for (int s = 0; s < 4; ++s) real[s] = tok[s] >= 0;
+    // the blocks of a BasicLayer all use shift 0 (SwinWNet.py:328), i.e. the SAME window partition: the rows of the window
+    // run through `depth` consecutive blocks without leaving the registers
+    for (int blk = 0; blk < p.depth; ++blk) {
+    const uint32_t* wb = w_s + blk * (G::W_ELEMS / 2);
+    const float* fb = f_s + blk * G::F_ELEMS;
+    const uint2* wq = reinterpret_cast<const uint2*>(wb + G::OFF_Q / 2) + lane;
+    const uint2* wk = reinterpret_cast<const uint2*>(wb + G::OFF_K / 2) + lane;
+    const uint4* wv = reinterpret_cast<const uint4*>(wb + G::OFF_V / 2) + lane;
+    const uint2* wp = reinterpret_cast<const uint2*>(wb + G::OFF_P / 2) + lane;
+    const uint2* w1 = reinterpret_cast<const uint2*>(wb + G::OFF_1 / 2) + lane;
+    const uint2* w2 = reinterpret_cast<const uint2*>(wb + G::OFF_2 / 2) + lane;
+    const float4* biasfrag = reinterpret_cast<const float4*>(fb + G::F_BIAS) + lane;
     uint32_t a1[2][KT][4];
     layer_norm(x, a1, real, true);
 
@@ -378,7 +383,7 @@ __global__ void __launch_bounds__(WB_THREADS, MINB) swin_warp_block_kernel(const
     layer_norm(x, a2, real, false);
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
-      const float2 b2 = *reinterpret_cast<const float2*>(f_s + 8 * j + 2 * t);
+      const float2 b2 = *reinterpret_cast<const float2*>(fb + 8 * j + 2 * t);
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
         x[mt][j][0] += b2.x; x[mt][j][1] += b2.y; x[mt][j][2] += b2.x; x[mt][j][3] += b2.y;
@@ -411,6 +416,7 @@ __global__ void __launch_bounds__(WB_THREADS, MINB) swin_warp_block_kernel(const
         wb_mma16(x[1][j], ah[1], bw.x, bw.y);
       }
     }
+    }   // blocks
     // ---- write the rows back ----
 #pragma unroll
     for (int s = 0; s < 4; ++s)
@@ -427,6 +433,7 @@ __global__ void __launch_bounds__(WB_THREADS, MINB) swin_warp_block_kernel(const
 int launch_swin_warp_block(WarpBlockParams p, int num_sms, cudaStream_t stream) {
   SWN_CHECK(p.nH == 3 && (p.C == 12 || p.C == 24), "swin_block_warp: only C in {12, 24} with 3 heads (got C=%d nH=%d)", p.C, p.nH);
   SWN_CHECK(p.B > 0 && p.H > 0 && p.W > 0, "swin_block_warp: empty input");
+  SWN_CHECK(p.depth >= 1 && p.depth <= 4, "swin_block_warp: depth %d not in 1..4", p.depth);
   p.nWy = (p.H + 4) / 5;
   p.nWx = (p.W + 4) / 5;
   const long long nw = (long long)p.B * p.nWy * p.nWx;
@@ -444,8 +451,8 @@ int launch_swin_warp_block(WarpBlockParams p, int num_sms, cudaStream_t stream) 
     SWN_CUDA(cudaGetLastError());
     return 0;
   };
-  if (p.C == 12) return go(swin_warp_block_kernel<12, SWN_WB_MINB12>, WbGeom<12>::W_ELEMS * 2 + WbGeom<12>::F_ELEMS * 4);
-  return go(swin_warp_block_kernel<24, SWN_WB_MINB24>, WbGeom<24>::W_ELEMS * 2 + WbGeom<24>::F_ELEMS * 4);
+  if (p.C == 12) return go(swin_warp_block_kernel<12, SWN_WB_MINB12>, (size_t)p.depth * (WbGeom<12>::W_ELEMS * 2 + WbGeom<12>::F_ELEMS * 4));
+  return go(swin_warp_block_kernel<24, SWN_WB_MINB24>, (size_t)p.depth * (WbGeom<24>::W_ELEMS * 2 + WbGeom<24>::F_ELEMS * 4));
 }
 
 }  // namespace swn

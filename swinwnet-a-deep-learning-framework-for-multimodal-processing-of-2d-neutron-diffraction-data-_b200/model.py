@@ -38,6 +38,7 @@ FUSED_ATTN = {(96, 3), (96, 6)}                       # instances of swin_attn_s
 # (C, heads) that run one warp per window on mma.sync register fragments (csrc/swin_warp.cu) instead of swin_fused_kernel;
 # SWN_WARP_BLOCK=0 keeps the tcgen05 block kernel for A/B measurements
 WARP_BLOCK = {(12, 3), (24, 3)} if os.environ.get("SWN_WARP_BLOCK", "1") != "0" else set()
+WARP_LAYER = os.environ.get("SWN_WARP_LAYER", "1") != "0"    # all blocks of such a BasicLayer in one launch
 
 
 def _check_infer(x):
@@ -280,6 +281,7 @@ class BasicLayer(nn.Module):
             SwinTransformerBlock(dim=dim, num_heads=num_heads, window_size=window_size, shift_size=0,  # SwinWNet.py:328
                                  mlp_ratio=mlp_ratio, qkv_bias=qkv_bias, drop=drop, attn_drop=attn_drop, drop_path=drop_path)
             for _ in range(depth)])
+        self._cache_warp = _PackCache()
 
     def run(self, x, resolution, inplace=False):
         """returns the layer output; with inplace=True the caller gives up x (it may be overwritten or returned)."""
@@ -287,6 +289,19 @@ class BasicLayer(nn.Module):
             for blk in self.blocks:
                 x = blk(x, resolution)
             return x
+        if (FUSED_BLOCK and WARP_LAYER and 1 <= len(self.blocks) <= 4 and x.shape[-1] == self.dim
+                and all((b.dim, b.num_heads) in WARP_BLOCK and b.shift_size == 0 for b in self.blocks)):
+            # C = 12 / 24: every block of the layer uses the same (unshifted) window partition -> ONE launch carries the rows
+            # of a window through all blocks in registers (csrc/swin_warp.cu)
+            B, L, C = x.shape
+            H, W = resolution
+            assert L == H * W, "input feature has wrong size"
+            packs = [b._packed_warp() for b in self.blocks]
+            Wpk, fpk = self._cache_warp.get([t for pk in packs for t in pk],
+                                            lambda: (torch.cat([pk[0] for pk in packs]), torch.cat([pk[1] for pk in packs])))
+            out = torch.empty_like(x)
+            ops.swin_block_warp(x, out, B, H, W, C, self.blocks[0].num_heads, self.blocks[0].norm1.eps, Wpk, fpk, len(self.blocks))
+            return out
         if FUSED_BLOCK and all((b.dim, b.num_heads) in FUSED_WHOLE and b.shift_size == 0 for b in self.blocks):
             # single-kernel blocks never run in place: ping-pong between two buffers
             spare = None

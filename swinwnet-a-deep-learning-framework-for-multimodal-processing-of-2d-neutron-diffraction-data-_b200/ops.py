@@ -111,12 +111,12 @@ def swin_block_fused(x, out, B, H, W, C, nH, eps, Wpk, fpk, do_mlp=True):
     _count("swin_block_fused")
 
 
-def swin_block_warp(x, out, B, H, W, C, nH, eps, Wpk, fpk):
-    """whole shift-0 Swin block for C = 12 / 24 (3 heads): one warp per window on mma.sync register fragments
-    (csrc/swin_warp.cu); out must not alias x."""
+def swin_block_warp(x, out, B, H, W, C, nH, eps, Wpk, fpk, depth=1):
+    """`depth` consecutive shift-0 Swin blocks for C = 12 / 24 (3 heads): one warp per window on mma.sync register
+    fragments (csrc/swin_warp.cu); Wpk / fpk = the blocks' packs concatenated; out must not alias x."""
     with _Launch(x, out, Wpk, fpk) as st:
-        _lib.check(_lib.load().swn_swin_block_warp(_ptr(x), _ptr(out), B, H, W, C, nH, eps, _ptr(Wpk), _ptr(fpk), st),
-                   "swn_swin_block_warp")
+        _lib.check(_lib.load().swn_swin_block_warp(_ptr(x), _ptr(out), B, H, W, C, nH, eps, _ptr(Wpk), _ptr(fpk), int(depth),
+                                                   st), "swn_swin_block_warp")
     _count("swin_block_warp")
 
 

@@ -337,6 +337,29 @@ def test_swin_block_warp(C, B, H, W):
         ops.swin_block_warp(xd, xd, B, H, W, C, nH, 1e-5, Wpk, fpk)
 
 
+@pytest.mark.parametrize("C,B,H,W,depth", [(12, 2, 13, 9, 2), (12, 1, 100, 190, 2), (24, 1, 32, 61, 2), (24, 2, 125, 240, 3),
+                                           (12, 1, 40, 65, 4)])
+def test_swin_block_warp_layer(C, B, H, W, depth):
+    """`depth` consecutive blocks (different weights) in one launch == the oracle blocks applied one after the other"""
+    nH = 3
+    x = rnd(B, H * W, C, seed=2) * 1.5 + 0.2
+    ref, Wl, fl = x, [], []
+    for i in range(depth):
+        sd, order = _block_sd(C, nH)
+        sd = {k: v * (1.0 + 0.05 * i) + (0.01 * i if k.endswith("bias") else 0.0) for k, v in sd.items()}
+        ref = O.swin_block(sd, "", ref, (H, W), nH, 0)
+        Wp, fp = packing.pack_warp_block(*[sd[k].to(DEV) for k in order], nH)
+        Wl.append(Wp)
+        fl.append(fp)
+    xd = x.to(DEV)
+    out = torch.full_like(xd, float("nan"))
+    ops.swin_block_warp(xd, out, B, H, W, C, nH, 1e-5, torch.cat(Wl), torch.cat(fl), depth)
+    torch.cuda.synchronize()
+    assert relerr(out, ref) <= TOL_BF16 / 4 * depth ** 0.5
+    with pytest.raises(RuntimeError, match="depth"):
+        ops.swin_block_warp(xd, out, B, H, W, C, nH, 1e-5, torch.cat(Wl), torch.cat(fl), 5)
+
+
 @pytest.mark.parametrize("nH,B,H,W", [(3, 2, 10, 15), (6, 1, 13, 9), (3, 1, 63, 120), (6, 2, 100, 101)])
 def test_swin_attn_stream_c96(nH, B, H, W):
     """streamed-weight C=96 attention-half kernel: x + proj(W-MSA(LN1 x)) against the oracle (padding, ragged last

@@ -79,6 +79,9 @@ for (L, C, nH, H, W) in SHAPES:
         out = torch.empty_like(x)
         ms = timeit(lambda: ops.swin_block_warp(x, out, B, H, W, C, nH, 1e-5, Wpk, fpk))
         report("wblk", M, C, ms, M * C * 8, (24.0 * C * C + 100.0 * C) * M)
+        W2, f2 = torch.cat([Wpk, Wpk]), torch.cat([fpk, fpk])
+        ms = timeit(lambda: ops.swin_block_warp(x, out, B, H, W, C, nH, 1e-5, W2, f2, 2))
+        report("wblk2", M, C, ms, M * C * 8, 2 * (24.0 * C * C + 100.0 * C) * M)
     if "fused" in a.ops and C == 96:
         shp = [(C,), (C,), (3 * C, C), (3 * C,), (81, nH), (C, C), (C,)]
         params = [torch.randn(*s, device=DEV) * 0.1 for s in shp]
