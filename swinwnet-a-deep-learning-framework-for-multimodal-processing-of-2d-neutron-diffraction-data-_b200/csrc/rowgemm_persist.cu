@@ -56,6 +56,9 @@ __global__ void __launch_bounds__(RP_THREADS, 1) rowgemm_persist_kernel(const Ro
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntiles = (p.M + TILE_M - 1) / TILE_M;
   const bool has_ln = p.a_mode == A_F32_LN;
+  // dense staging (rows contiguous in global memory, copied 32 at a time): the row stride is a multiple of 128 bytes for the
+  // widths served here, so thread-per-row readers start at a row-dependent 8-column group to spread the shared-memory banks
+  const bool dense = rs == K * esz;
 
   if (threadIdx.x == 0) {
     mbar_init(&sh->w_full, 1);
@@ -106,8 +109,15 @@ __global__ void __launch_bounds__(RP_THREADS, 1) rowgemm_persist_kernel(const Ro
       __syncwarp();
       uint8_t* dst = stg + s * TILE_M * rs;
       const uint8_t* src = reinterpret_cast<const uint8_t*>(p.A);
-      for (int r = lane; r < rows; r += 32)
-        bulk_g2s(dst + r * rs, src + (m0 + r) * (long long)p.lda * esz, (uint32_t)(K * esz), &sh->in_full[s]);
+      if (dense) {
+        // contiguous rows: one copy per 32 rows (a bulk copy costs ~31 ns of the SM's copy engine whatever its size up to
+        // ~1 KB — tools/micro/tma_rate.cu — so 384-byte rows copied one by one cap the kernel at 1.9 TB/s of input)
+        if (lane * 32 < rows)
+          bulk_g2s(dst + lane * 32 * rs, src + (m0 + lane * 32) * (long long)rs, (uint32_t)(min(32, rows - lane * 32) * rs), &sh->in_full[s]);
+      } else {
+        for (int r = lane; r < rows; r += 32)
+          bulk_g2s(dst + r * rs, src + (m0 + r) * (long long)p.lda * esz, (uint32_t)(K * esz), &sh->in_full[s]);
+      }
       if (rrs) {
         uint8_t* rdst = rstg + s * TILE_M * rrs;
         for (int r = lane; r < rows; r += 32)
@@ -164,8 +174,11 @@ __global__ void __launch_bounds__(RP_THREADS, 1) rowgemm_persist_kernel(const Ro
       if (has_ln && row_ok) {
         const float x0 = *reinterpret_cast<const float*>(src);
         float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int c4 = 0; c4 < K / 4; ++c4) {
-          const float4 v = *reinterpret_cast<const float4*>(src + c4 * 16);
+        const int n4 = K / 4;
+        int cr = dense ? row % n4 : 0;
+        for (int c4 = 0; c4 < n4; ++c4) {
+          const float4 v = *reinterpret_cast<const float4*>(src + cr * 16);
+          if (++cr == n4) cr = 0;
           const float d0 = v.x - x0, d1 = v.y - x0, d2 = v.z - x0, d3 = v.w - x0;
           s1[0] += d0; s1[1] += d1; s1[2] += d2; s1[3] += d3;
           s2[0] = fmaf(d0, d0, s2[0]); s2[1] = fmaf(d1, d1, s2[1]); s2[2] = fmaf(d2, d2, s2[2]); s2[3] = fmaf(d3, d3, s2[3]);
@@ -176,7 +189,11 @@ __global__ void __launch_bounds__(RP_THREADS, 1) rowgemm_persist_kernel(const Ro
         mean = x0 + m1;
         rstd = rsqrtf(fmaxf(m2 - m1 * m1, 0.f) + p.ln_eps);
       }
-      for (int k = 0; k < K16; k += 8) {
+      const int ng = K16 >> 3;
+      int gr = dense ? row % ng : 0;
+      for (int q = 0; q < ng; ++q) {
+        const int k = gr * 8;
+        if (++gr == ng) gr = 0;
         uint32_t pk[4] = {0u, 0u, 0u, 0u};
         if (row_ok && k < K) {
           if (is_bf16) {
@@ -323,6 +340,9 @@ __global__ void __launch_bounds__(RP_THREADS, 1) rowgemm_persist_kernel(const Ro
 // returns 0 and launches if the shape qualifies; returns -1 (no error set) if the caller should use rowgemm.cu
 int launch_rowgemm_persist(RowGemmParams p, int num_sms, cudaStream_t stream) {
   if (p.a_mode == A_MERGE_LN || p.e_mode == E_EXPAND) return -1;
+#ifdef SWN_RP_NO_WIDE_RES
+  if (p.e_mode == E_F32 && p.res && p.nchunks * p.n_valid >= 128) return -1;   // A/B: rowgemm.cu's transposed residual epilogue
+#endif
   const int esz = p.a_mode == A_BF16 ? 2 : 4;
   // rows shorter than 192 B make the per-row bulk copies (~60 cycles each) the bottleneck: measured slower than rowgemm.cu
   if (p.K * esz > 400 || p.K * esz < 192 || p.K % 4 != 0 || (p.lda * esz) % 16 != 0 || (p.K * esz) % 16 != 0) return -1;
@@ -331,7 +351,7 @@ int launch_rowgemm_persist(RowGemmParams p, int num_sms, cudaStream_t stream) {
   if (w_bytes > 80 * 1024) return -1;
   auto padded = [](int bytes) { int ch = (bytes + 15) / 16; return (ch + ((ch & 1) ? 0 : 1)) * 16; };
   const int n_total = p.nchunks * p.n_valid;
-  p.stg_stride = padded(p.K * esz);
+  p.stg_stride = (p.lda == p.K && (p.K * esz) % 128 == 0) ? p.K * esz : padded(p.K * esz);   // dense rows: 32 rows per bulk copy
   p.res_stride = (p.e_mode == E_F32 && p.res && n_total * 4 <= 400 && p.ldres % 4 == 0 && (n_total * 4) % 16 == 0) ? padded(n_total * 4) : 0;
   const int nt32 = (p.NT + 31) & ~31;
   int nacc = 512 / nt32;
