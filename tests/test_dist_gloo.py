@@ -66,9 +66,10 @@ def _grad_worker(rank, world, port, out):
     h = model["enc"](x)
     loss = (model["dec"](h) ** 2).mean() if rank == 0 else (h ** 2).mean()   # rank 1 never touches "dec": grad None there
     loss.backward()
-    local = {n: (None if p.grad is None else p.grad.clone()) for n, p in model.named_parameters()}
+    # plain lists through the queue: tensors travel as shared-memory handles that die with this process
+    local = {n: (None if p.grad is None else p.grad.tolist()) for n, p in model.named_parameters()}
     n_red = red.reduce()
-    out.put((rank, n_red, local, {n: (None if p.grad is None else p.grad.clone()) for n, p in model.named_parameters()}))
+    out.put((rank, n_red, local, {n: (None if p.grad is None else p.grad.tolist()) for n, p in model.named_parameters()}))
     dist.destroy_process_group()
 
 
@@ -85,6 +86,7 @@ def test_grad_reducer_buckets_average_and_tolerate_missing_grads():
         p.join(timeout=60)
         assert p.exitcode == 0
     (_, n0, loc0, red0), (_, n1, loc1, red1) = res
+    loc0, red0, loc1, red1 = [{k: (None if v is None else torch.tensor(v)) for k, v in d.items()} for d in (loc0, red0, loc1, red1)]
     assert n0 == n1 == 6 * 5 + 5 + 5 * 3 + 3
     for name in red0:
         if name.startswith(("unused", "frozen")):

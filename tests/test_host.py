@@ -252,3 +252,141 @@ def test_npy_batch_ingestion_and_pathlike_checkpoint(tmp_path):
     torch.save({"state_dict": {"module." + k: v for k, v in m.state_dict().items()}}, tmp_path / "ck.pth")
     m2 = CK.build_model_from_checkpoint(tmp_path / "ck.pth")           # pathlib.Path
     assert type(m2).__name__ == "SwinUNet" and len(m2.state_dict()) == len(m.state_dict())
+
+
+def test_warp_block_packing_replays_the_kernel_dataflow():
+    """packing.pack_warp_block (host side of csrc/swin_warp.cu): a lane-level replay of the kernel's mma.sync fragment
+    dataflow in fp32 torch — m16n8k16 operand / accumulator layouts written out independently here from the PTX
+    definition — turns one 25-token window (20 real + 5 zero-padded tokens) into the oracle's q (scaled), k, v, the
+    attention output, and the whole block output."""
+    import math
+    torch.manual_seed(1)
+    lane = torch.arange(32)
+    g, t = lane // 4, lane % 4
+
+    def mma(Af, Bf, Cf):            # Af [32, 8] (a0..a3 pairs), Bf [32, 4] (b0, b1 pairs), Cf [32, 4]
+        A, Bm = torch.zeros(16, 16), torch.zeros(16, 8)
+        for r in range(4):
+            for e in range(2):
+                A[g + 8 * (r % 2), 2 * t + e + 8 * (r // 2)] = Af[:, 2 * r + e]
+        for r in range(2):
+            for e in range(2):
+                Bm[2 * t + e + 8 * r, g] = Bf[:, 2 * r + e]
+        Cm = A @ Bm
+        out = Cf.clone()
+        for i in range(4):
+            out[:, i] += Cm[g + 8 * (i // 2), 2 * t + i % 2]
+        return out
+
+    for C in (12, 24):
+        nH, hd = 3, C // 3
+        K16, KT, NJ = packing.warp_block_geometry(C)
+        shp = [(C,), (C,), (3 * C, C), (3 * C,), (81, nH), (C, C), (C,), (C,), (C,), (4 * C, C), (4 * C,), (C, 4 * C), (C,)]
+        prm = [torch.randn(*s) * (s[-1] ** -0.5 if len(s) == 2 else 0.2) + (1.0 if i in (0, 7) else 0.0) for i, s in enumerate(shp)]
+        n1w, n1b, Wqkv, bqkv, table, Wproj, bproj, n2w, n2b, W1, b1, W2, b2 = prm
+        Wpk, fpk = packing.pack_warp_block(*prm, nH)
+        Wpk = Wpk.float()
+        sizes = [KT * NJ * 128, KT * NJ * 128, KT * KT * 256, KT * NJ * 128, KT * (C // 2) * 128, (C // 4) * NJ * 128]
+        assert Wpk.numel() == sum(sizes) and fpk.numel() == K16 + nH * 1024      # WbGeom::W_ELEMS / F_ELEMS
+        Q, K, V, P, F1, F2 = torch.split(Wpk, sizes)
+        Q, K, P = [m.view(KT, NJ, 32, 4) for m in (Q, K, P)]
+        V, F1, F2 = V.view(KT, KT, 32, 8), F1.view(KT, C // 2, 32, 4), F2.view(C // 4, NJ, 32, 4)
+        bias_frag = fpk[K16:].view(nH, 2, 4, 32, 4)
+        # a 4 x 5 image: one window, its fifth row is zero padding (AFTER norm1) — oracle reference
+        H, W = 4, 5
+        x = torch.randn(1, H * W, C) * 1.5 + 0.3
+        sd = dict(zip(["norm1.weight", "norm1.bias", "attn.qkv.weight", "attn.qkv.bias", "attn.relative_position_bias_table",
+                       "attn.proj.weight", "attn.proj.bias", "norm2.weight", "norm2.bias", "mlp.0.weight", "mlp.0.bias",
+                       "mlp.3.weight", "mlp.3.bias"], prm))
+        ref = O.swin_block(sd, "", x, (H, W), nH, 0)[0]
+        # ---- the kernel, lane by lane: rows in accumulator layout xr[mt][j] = [32, 4] ----
+        rows = torch.zeros(32, K16)
+        rows[:20, :C] = x[0]
+        real = torch.zeros(32, dtype=torch.bool)
+        real[:20] = True
+
+        def to_frag(m):             # [32 rows, K16] -> acc-layout list [mt][j] of [32 lanes, 4]
+            return [[torch.stack([m[16 * mt + g + 8 * (i // 2), 8 * j + 2 * t + i % 2] for i in range(4)], 1)
+                     for j in range(K16 // 8)] for mt in range(2)]
+
+        def from_frag(fr, ncols):
+            m = torch.zeros(32, ncols)
+            for mt in range(2):
+                for j in range(ncols // 8):
+                    for i in range(4):
+                        m[16 * mt + g + 8 * (i // 2), 8 * j + 2 * t + i % 2] = fr[mt][j][:, i]
+            return m
+
+        def a_frags(fr):            # acc-layout tiles -> A fragments [mt][kt] of [32, 8]
+            return [[torch.cat([fr[mt][2 * kt][:, 0:2], fr[mt][2 * kt][:, 2:4], fr[mt][2 * kt + 1][:, 0:2], fr[mt][2 * kt + 1][:, 2:4]], 1)
+                     for kt in range(KT)] for mt in range(2)]
+
+        def layer_norm_frags(m, first):
+            mu = m[:, :C].mean(-1, keepdim=True)
+            xn = (m[:, :C] - mu) * torch.rsqrt(m[:, :C].var(-1, unbiased=False, keepdim=True) + 1e-5)
+            z = torch.zeros(32, K16)
+            z[:, :C] = xn * (real[:, None] if first else 1.0)
+            z[:, C] = 1.0
+            z[:, C + 1] = real.float() if first else 0.0
+            return a_frags(to_frag(z))
+
+        a1 = layer_norm_frags(rows, True)
+        zero = torch.zeros(32, 4)
+        q = [[None] * NJ for _ in range(2)]
+        k = [[None] * NJ for _ in range(2)]
+        for n in range(NJ):
+            for mt in range(2):
+                qc, kc = zero, zero
+                for kt in range(KT):
+                    qc, kc = mma(a1[mt][kt], Q[kt, n], qc), mma(a1[mt][kt], K[kt, n], kc)
+                q[mt][n], k[mt][n] = qc, kc
+        qkv_ref = O.linear(torch.cat([O.layer_norm(x[0], n1w, n1b), torch.zeros(5, C)]), Wqkv, bqkv)   # padded tokens: zeros after norm1
+        qs = hd ** -0.5 * math.log2(math.e)
+        tol = 3e-3 * qkv_ref.abs().max()
+        assert (from_frag(q, NJ * 8)[:25, :C] - qkv_ref[:, :C] * qs).abs().max() <= tol * qs
+        assert (from_frag(k, NJ * 8)[:25, :C] - qkv_ref[:, C:2 * C]).abs().max() <= tol
+        # v^T = Wv xn^T: A operand = weight fragments, B operand = the LayerNorm fragments of token tile nt
+        vT = torch.zeros(K16, 32)
+        for mv in range(KT):
+            for nt in range(4):
+                vc = zero
+                for kt in range(KT):
+                    af = a1[nt // 2][kt]
+                    vc = mma(V[mv, kt], torch.cat([af[:, 2 * (nt % 2):2 * (nt % 2) + 2], af[:, 4 + 2 * (nt % 2):6 + 2 * (nt % 2)]], 1), vc)
+                for i in range(4):
+                    vT[16 * mv + g + 8 * (i // 2), 8 * nt + 2 * t + i % 2] = vc[:, i]
+        assert (vT[:C, :25].t() - qkv_ref[:, 2 * C:]).abs().max() <= tol
+        # softmax(q k^T + bias) v on the reconstructed matrices (the bias image carries log2(e) and the key mask)
+        qm, km = from_frag(q, NJ * 8), from_frag(k, NJ * 8)
+        o = torch.zeros(32, K16)
+        for h in range(nH):
+            bias = torch.zeros(32, 32)
+            for mt in range(2):
+                for nt in range(4):
+                    for i in range(4):
+                        bias[16 * mt + g + 8 * (i // 2), 8 * nt + 2 * t + i % 2] = bias_frag[h, mt, nt, :, i]
+            s = qm[:, h * hd:(h + 1) * hd] @ km[:, h * hd:(h + 1) * hd].t() + bias
+            pr = torch.exp2(s - s.max(-1, keepdim=True).values)
+            o[:, h * hd:(h + 1) * hd] = (pr @ vT[h * hd:(h + 1) * hd].t()) / pr.sum(-1, keepdim=True)
+        o[:, C] = 1.0
+        ao = a_frags(to_frag(o))
+        x1 = to_frag(rows)
+        for mt in range(2):
+            for j in range(NJ):
+                for kt in range(KT):
+                    x1[mt][j] = mma(ao[mt][kt], P[kt, j], x1[mt][j])
+        x1m = torch.zeros(32, K16)
+        x1m[:, :NJ * 8] = from_frag([r[:NJ] for r in x1], NJ * 8)
+        a2 = layer_norm_frags(x1m, False)
+        y = to_frag(x1m + torch.cat([fpk[:K16]])[None, :])
+        for u in range(C // 4):
+            for mt in range(2):
+                h0, h1 = zero, zero
+                for kt in range(KT):
+                    h0, h1 = mma(a2[mt][kt], F1[kt, 2 * u], h0), mma(a2[mt][kt], F1[kt, 2 * u + 1], h1)
+                ge = lambda v: torch.nn.functional.gelu(v)
+                ah = torch.cat([ge(h0[:, 0:2]), ge(h0[:, 2:4]), ge(h1[:, 0:2]), ge(h1[:, 2:4])], 1)
+                for j in range(NJ):
+                    y[mt][j] = mma(ah, F2[u, j], y[mt][j])
+        out = from_frag([r[:NJ] for r in y], NJ * 8)[:20, :C]
+        assert (out - ref).abs().max() <= 5e-3 * ref.abs().max(), (C, (out - ref).abs().max(), ref.abs().max())

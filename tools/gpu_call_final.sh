@@ -8,7 +8,10 @@ timeout 1800 python -m pytest tests -m gpu -q -p no:cacheprovider > $O/final_tes
 echo "tests rc=$?"; tail -5 $O/final_tests.log
 timeout 900 python bench.py > $O/final_bench.json 2> $O/final_bench.err
 echo "bench rc=$?"; tail -2 $O/final_bench.err
+# launches of one step (bench.py counts them): the ncu pass skips the 3 warm-up steps and captures exactly one step
+L=$(python -c "import json; d = json.load(open('$O/final_bench.json')); print(d['gpu_launches'] // d['steps'])")
+echo "launches per step: $L"
 timeout 600 python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-library-bar --no-parity-check > $O/final_plain.log 2>&1 && \
-timeout 1500 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:swn -s 660 -c 222 --csv --log-file $O/final_step.csv \
+timeout 1500 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:swn -s $((3 * L)) -c $L --csv --log-file $O/final_step.csv \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-library-bar --no-parity-check > $O/final_ncu.log 2>&1
 echo "ncu rc=$?"; tail -2 $O/final_ncu.log

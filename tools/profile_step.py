@@ -42,6 +42,8 @@ if a.table:
                 key = f"B={args[4]} {args[5]}x{args[6]} C={args[7]} nH={args[8]}"
             elif name == "swin_block_fused":
                 key = f"B={args[2]} {args[3]}x{args[4]} C={args[5]} nH={args[6]}"
+            elif name == "swin_block_warp":
+                key = f"B={args[2]} {args[3]}x{args[4]} C={args[5]} depth={args[10] if len(args) > 10 else kw.get('depth', 1)}"
             elif name == "swin_block_small":
                 key = f"B={args[2]} {args[3]}x{args[4]} C={args[5]}"
             elif name == "cross_attention":
@@ -55,7 +57,7 @@ if a.table:
             records.append((name, key, e0, e1))
             return r
         setattr(ops, name, timed)
-    for n in ("rowgemm", "mlp", "window_attention", "swin_block_small", "swin_block_fused", "cross_attention", "patch_embed", "seg_head",
+    for n in ("rowgemm", "mlp", "window_attention", "swin_block_small", "swin_block_fused", "swin_block_warp", "cross_attention", "patch_embed", "seg_head",
               "recon_head", "copy_cols", "sigmoid_mask", "normalize"):
         wrap(n)
 
