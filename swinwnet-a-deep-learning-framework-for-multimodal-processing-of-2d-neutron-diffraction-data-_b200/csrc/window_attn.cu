@@ -251,6 +251,197 @@ __global__ void __launch_bounds__(WA_THREADS) window_attn_kernel(const WinAttnPa
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// shift == 0, head_dim 16 / 32 (every W-MSA of the shipped models at C >= 192): ONE WARP PER WINDOW, no shared-memory
+// staging and no block barrier.  The warp walks over the heads of its window; q, k and v of a head are loaded from global
+// memory straight into mma.sync fragments with ONE 16-byte (head_dim 32) or 8-byte (16) load per row and operand — possible
+// because the contraction index of q k^T and the column index of P v may be permuted (see ldv below; 4-byte loads in the
+// canonical fragment order were measured slower than the staged kernel: 8 sectors per instruction saturate the L1 tag
+// stage) — v is turned into the B operand of P v with movmatrix.trans, the row sums come from P x ones, and the
+// relative-position bias image of every head sits in shared memory in accumulator-fragment order (built once per
+// persistent CTA from the [81, nH] table).  The staged kernel above paid three CTA barriers, the table transpose and the
+// token index math per group of 1-2 windows and reached 35 % of the HBM roofline.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int WW_THREADS = 256;
+
+__device__ __forceinline__ uint32_t ww_movm_trans(uint32_t a) {
+  uint32_t d;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
+  return d;
+}
+__device__ __forceinline__ void ww_mma(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32." SWN_MMA_T "." SWN_MMA_T ".f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int HD>
+__global__ void __launch_bounds__(WW_THREADS, 2) window_attn_warp_kernel(const WinAttnParams p, int nWy, int nWx, int n_units, int hsplit) {
+  constexpr int KS = HD / 16, NR = HD / 8, VEC = HD / 4;   // k-steps of q k^T, registers (column pairs) / columns per lane and row
+  extern __shared__ __align__(16) uint8_t ww_smem[];
+  float* bias_f = reinterpret_cast<float*>(ww_smem);           // [nH][2 mt][4 nt][32 lanes][4]
+  const int C = p.C, nH = p.nH, C3 = 3 * p.C;
+  for (int i = threadIdx.x; i < nH * 1024; i += WW_THREADS) {
+    const int e = i & 3, ln = (i >> 2) & 31, tile = (i >> 7) & 7, h = i >> 10;
+    const int row = (tile >> 2) * 16 + (ln >> 2) + (e >> 1) * 8, key = (tile & 3) * 8 + (ln & 3) * 2 + (e & 1);
+    float v = 0.f;
+    if (key >= WN) v = -1e30f;                                  // key columns 25..31: padding of the mma tile
+    else if (row < WN) v = __ldg(p.rpb_table + ((row / WS - key / WS + WS - 1) * (2 * WS - 1) + (row % WS - key % WS + WS - 1)) * nH + h) * 1.4426950408889634f;
+    bias_f[i] = v;
+  }
+  __syncthreads();
+  const float4* bias4 = reinterpret_cast<const float4*>(bias_f);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
+  const float sl2 = rsqrtf((float)HD) * 1.4426950408889634f;
+  const uint32_t ONE_ONE = pack_op(1.f, 1.f);
+  const int nWin2 = nWy * nWx;
+  // work unit = (window, group of nH / hsplit heads): small inputs are split by heads so that every warp slot has work
+  const int hpg = nH / hsplit;
+  for (int unit = blockIdx.x * (WW_THREADS / 32) + warp; unit < n_units; unit += gridDim.x * (WW_THREADS / 32)) {
+    const int win = unit / hsplit, h_beg = (unit - win * hsplit) * hpg;
+    const int b = win / nWin2, wr = win - b * nWin2;
+    const int wy = wr / nWx, wx = wr - wy * nWx;
+    // row slot s = 0..3 of this lane: token i = 8 s + g of the window.  kind 0: real token, 1: zero-padded token (q/k/v =
+    // the qkv bias, SwinWNet.py:254), 2: padding of the second mma tile (zeros; masked as a key by the bias image)
+    const op_t* rowp[4];
+    long long otok[4];
+    int kind[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const int i = 8 * s + g;
+      kind[s] = 2;
+      rowp[s] = p.qkv;
+      otok[s] = 0;
+      if (i < WN) {
+        const int Y = wy * WS + i / WS, X = wx * WS + i % WS;
+        kind[s] = 1;
+        if (Y < p.H && X < p.W) {
+          kind[s] = 0;
+          otok[s] = ((long long)b * p.H + Y) * p.W + X;
+          rowp[s] = p.qkv + otok[s] * C3;
+        }
+      }
+    }
+    // NR consecutive column pairs (8 or 4 columns: one 16- or 8-byte load) of row slot s.  The k index of q k^T and the
+    // column index of P v may be permuted freely as long as both operands agree, so lane (g, t) takes columns
+    // [VEC t, VEC t + VEC) of its rows: register r is the pair VEC t + 2r, the mma k slots (2t, 2t+1) and (2t+8, 2t+9) of
+    // k-step ks are registers 2ks and 2ks+1 — for q and k alike
+    auto ldv = [&](int s, int col, uint32_t (&r)[NR]) {
+      if (kind[s] == 0) {
+        if constexpr (NR == 4) {
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(rowp[s] + col));
+          r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
+        } else {
+          const uint2 v = __ldg(reinterpret_cast<const uint2*>(rowp[s] + col));
+          r[0] = v.x; r[1] = v.y;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < NR; ++i)
+          r[i] = kind[s] == 1 ? pack_op(__ldg(p.qkv_bias + col + 2 * i), __ldg(p.qkv_bias + col + 2 * i + 1)) : 0u;
+      }
+    };
+    for (int h = h_beg; h < h_beg + hpg; ++h) {
+      const int qc = h * HD + VEC * t4, kc = C + qc, vc = 2 * C + qc;
+      // ---- q, k, v rows straight from global memory (one vector load per row slot and operand) ----
+      uint32_t qr[4][NR], kr[4][NR], vr[4][NR];
+#pragma unroll
+      for (int s4 = 0; s4 < 4; ++s4) {
+        ldv(s4, qc, qr[s4]);
+        ldv(s4, kc, kr[s4]);
+      }
+#pragma unroll
+      for (int s4 = 0; s4 < 4; ++s4) ldv(s4, vc, vr[s4]);
+      uint32_t qa[2][KS][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+          qa[mt][ks][0] = qr[2 * mt][2 * ks];
+          qa[mt][ks][1] = qr[2 * mt + 1][2 * ks];
+          qa[mt][ks][2] = qr[2 * mt][2 * ks + 1];
+          qa[mt][ks][3] = qr[2 * mt + 1][2 * ks + 1];
+        }
+      // ---- S = q k^T * hd^-0.5 log2(e) + bias image ----
+      float sc[2][4][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          sc[mt][nt][0] = sc[mt][nt][1] = sc[mt][nt][2] = sc[mt][nt][3] = 0.f;
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks) ww_mma(sc[mt][nt], qa[mt][ks], kr[nt][2 * ks], kr[nt][2 * ks + 1]);
+          const float4 b4 = bias4[(h * 8 + mt * 4 + nt) * 32 + lane];
+          sc[mt][nt][0] = fmaf(sc[mt][nt][0], sl2, b4.x);
+          sc[mt][nt][1] = fmaf(sc[mt][nt][1], sl2, b4.y);
+          sc[mt][nt][2] = fmaf(sc[mt][nt][2], sl2, b4.z);
+          sc[mt][nt][3] = fmaf(sc[mt][nt][3], sl2, b4.w);
+        }
+      // ---- P = 2^(s - rowmax) as A fragments (no exponential for the key columns 25, 27, 29, 31: padding in every lane) ----
+      uint32_t pa[2][2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        float m0 = fmaxf(fmaxf(sc[mt][0][0], sc[mt][0][1]), fmaxf(sc[mt][1][0], sc[mt][1][1]));
+        m0 = fmaxf(m0, fmaxf(fmaxf(sc[mt][2][0], sc[mt][2][1]), sc[mt][3][0]));
+        float m1 = fmaxf(fmaxf(sc[mt][0][2], sc[mt][0][3]), fmaxf(sc[mt][1][2], sc[mt][1][3]));
+        m1 = fmaxf(m1, fmaxf(fmaxf(sc[mt][2][2], sc[mt][2][3]), sc[mt][3][2]));
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+        pa[mt][0][0] = pack_op(ex2_approx(sc[mt][0][0] - m0), ex2_approx(sc[mt][0][1] - m0));
+        pa[mt][0][1] = pack_op(ex2_approx(sc[mt][0][2] - m1), ex2_approx(sc[mt][0][3] - m1));
+        pa[mt][0][2] = pack_op(ex2_approx(sc[mt][1][0] - m0), ex2_approx(sc[mt][1][1] - m0));
+        pa[mt][0][3] = pack_op(ex2_approx(sc[mt][1][2] - m1), ex2_approx(sc[mt][1][3] - m1));
+        pa[mt][1][0] = pack_op(ex2_approx(sc[mt][2][0] - m0), ex2_approx(sc[mt][2][1] - m0));
+        pa[mt][1][1] = pack_op(ex2_approx(sc[mt][2][2] - m1), ex2_approx(sc[mt][2][3] - m1));
+        pa[mt][1][2] = pack_op(ex2_approx(sc[mt][3][0] - m0), 0.f);
+        pa[mt][1][3] = pack_op(ex2_approx(sc[mt][3][2] - m1), 0.f);
+      }
+      // ---- O = P v, row sums = P x ones ----
+      float od[2][4] = {};
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        ww_mma(od[0], pa[0][ks], ONE_ONE, ONE_ONE);
+        ww_mma(od[1], pa[1][ks], ONE_ONE, ONE_ONE);
+      }
+      float inv[2][2];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        inv[mt][0] = rcp_approx(od[mt][0]);
+        inv[mt][1] = rcp_approx(od[mt][2]);
+      }
+      // v register r of key tile j is an 8x8 matrix [key][column VEC (c / 2) + 2r + c % 2]; transposed it is the B operand of
+      // output tile r, whose accumulator columns (2t, 2t+1) are the columns VEC t + 2r, + 1: the NR tiles of a lane are
+      // VEC consecutive columns of its rows -> one vector store per row
+      uint32_t orow[4][NR];
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        float o[2][4] = {};
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          const uint32_t b0 = ww_movm_trans(vr[2 * ks][r]), b1 = ww_movm_trans(vr[2 * ks + 1][r]);
+          ww_mma(o[0], pa[0][ks], b0, b1);
+          ww_mma(o[1], pa[1][ks], b0, b1);
+        }
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          orow[2 * mt][r] = pack_op(o[mt][0] * inv[mt][0], o[mt][1] * inv[mt][0]);
+          orow[2 * mt + 1][r] = pack_op(o[mt][2] * inv[mt][1], o[mt][3] * inv[mt][1]);
+        }
+      }
+#pragma unroll
+      for (int s4 = 0; s4 < 4; ++s4)
+        if (kind[s4] == 0) {
+          op_t* dst = p.out + otok[s4] * C + qc;
+          if constexpr (NR == 4) *reinterpret_cast<uint4*>(dst) = make_uint4(orow[s4][0], orow[s4][1], orow[s4][2], orow[s4][3]);
+          else *reinterpret_cast<uint2*>(dst) = make_uint2(orow[s4][0], orow[s4][1]);
+        }
+    }
+  }
+}
+
+
 int launch_window_attn(WinAttnParams p, cudaStream_t stream) {
   SWN_CHECK(p.C % p.nH == 0, "window_attn: C %% nH != 0");
   const int hd = p.C / p.nH;
@@ -260,6 +451,33 @@ int launch_window_attn(WinAttnParams p, cudaStream_t stream) {
               "window_attn: shift>0 needs H,W multiples of the window size (reference semantics undefined otherwise)");
   const int nWy = (p.H + WS - 1) / WS, nWx = (p.W + WS - 1) / WS;
   const long long n_windows = (long long)p.B * nWy * nWx;
+#ifndef SWN_WA_WARP
+#define SWN_WA_WARP 1
+#endif
+  if (SWN_WA_WARP && p.shift == 0 && (hd == 16 || hd == 32) && (size_t)p.nH * 4096 <= 100 * 1024 && n_windows * p.nH < (1ll << 31)) {
+    const size_t smem_w = (size_t)p.nH * 4096;
+    auto go_w = [&](auto kern) -> int {
+      SWN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
+      int dev = 0, sms = 148, occ = 0;
+      SWN_CUDA(cudaGetDevice(&dev));
+      SWN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      SWN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WW_THREADS, smem_w));
+      SWN_CHECK(occ > 0, "window_attn: warp kernel does not fit on an SM");
+      long long grid = (long long)sms * occ;
+      int hsplit = 1;                      // split the heads of a window over several warps until every warp slot has ~3 units
+      while (hsplit < p.nH && n_windows * hsplit < 3 * grid * (WW_THREADS / 32)) {
+        ++hsplit;
+        while (p.nH % hsplit) ++hsplit;
+      }
+      const long long n_units = n_windows * hsplit;
+      const long long need = (n_units + WW_THREADS / 32 - 1) / (WW_THREADS / 32);
+      if (grid > need) grid = need;
+      kern<<<(unsigned)grid, WW_THREADS, smem_w, stream>>>(p, nWy, nWx, (int)n_units, hsplit);
+      SWN_CUDA(cudaGetLastError());
+      return 0;
+    };
+    return hd == 16 ? go_w(window_attn_warp_kernel<16>) : go_w(window_attn_warp_kernel<32>);
+  }
   // padded row stride (bf16 elements): multiple of 8 (16-byte rows for ldmatrix), (RS/2) % 8 == 4 when possible
   int RS = ((3 * p.C + 7) & ~7) + 8;
   if (((RS / 2) & 7) == 0) RS += 8;

@@ -158,13 +158,18 @@ def _win_attn_ref(qkv, bias, table, B, H, W, C, nH, shift):
 
 @pytest.mark.parametrize("C,nH,H,W,shift", [(48, 3, 10, 15, 0), (96, 6, 7, 11, 0), (384, 24, 4, 6, 0), (384, 12, 8, 5, 0),
                                             (192, 6, 5, 10, 0), (24, 3, 10, 10, 0), (12, 3, 12, 9, 0), (48, 3, 10, 15, 2),
-                                            (96, 3, 5, 5, 3)])
+                                            (96, 3, 5, 5, 3),
+                                            # warp-per-window kernel (shift 0, head_dim 16 / 32): padded windows in y and x, an image
+                                            # smaller than a window, many windows per warp
+                                            (192, 6, 63, 120, 0), (192, 12, 32, 60, 0), (384, 12, 32, 61, 0), (384, 24, 16, 30, 0),
+                                            (96, 3, 3, 4, 0), (96, 6, 125, 240, 0)])
 def test_window_attention(C, nH, H, W, shift):
     B = 2
     qkv = rnd(B * H * W, 3 * C, seed=1).to(OPD)
     bias, table = rnd(3 * C, seed=2, scale=0.3), rnd(81, nH, seed=3, scale=0.5)
     ref = _win_attn_ref(qkv.float(), bf(bias), table, B, H, W, C, nH, shift)
     out = torch.empty(B * H * W, C, device=DEV, dtype=OPD)
+    out.fill_(float("nan"))
     ops.window_attention(qkv.to(DEV), out, bias.to(DEV), table.to(DEV), B, H, W, C, nH, shift)
     torch.cuda.synchronize()
     assert relerr(out, ref) <= 1e-2
