@@ -59,6 +59,12 @@ constexpr int MP_LN_WARPS = 4;
 #define SWN_MP_FINAL_LN 0
 #endif
 constexpr int MP_EPI_THREADS = 128 * MP_EPI_SPLIT;
+// Staged variant with TWO A tiles: LayerNorm of tile i+1 runs while the GEMMs of tile i are in flight instead of between the
+// last GEMM1 of tile i and the first of tile i+1.  Needs 2 more k-blocks of shared memory (32 KB at C = 96: only with 64-column
+// hidden chunks, -DSWN_MLP96_HC=64).
+#ifndef SWN_MP_NA2
+#define SWN_MP_NA2 0
+#endif
 
 struct MpSmem {
   uint64_t full[8], empty[8];
@@ -87,7 +93,7 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
   const int w1_bytes = HC * 128, w2_bytes = TR * 128;
   const int rs = p.row_stride;  // staging row stride in bytes (odd number of 16-byte chunks)
 
-  constexpr int NA = DIRECT ? 2 : 1;                   // A-tile buffers
+  constexpr int NA = (DIRECT || SWN_MP_NA2) ? 2 : 1;   // A-tile buffers
   constexpr int LN_FIRST = DIRECT ? 2 : 4;             // DIRECT: no input producer -> warps 2..7 run the LayerNorm prologue
   constexpr int LN_WARPS = DIRECT ? 6 : MP_LN_WARPS;
   uint8_t* a_smem = smem;
@@ -307,8 +313,11 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
         mbar_arrive_warp(&sh->a_full[ab]);
         continue;
       }
-      if (warp == 4) { MP_TIMED(12, mbar_wait(&sh->in_full[s], ((uint32_t)it >> 1) & 1u)); MP_TIMED(13, mbar_wait(&sh->a_empty[0], ((uint32_t)it & 1u) ^ 1u)); }
-      else { mbar_wait(&sh->in_full[s], ((uint32_t)it >> 1) & 1u); mbar_wait(&sh->a_empty[0], ((uint32_t)it & 1u) ^ 1u); }
+      const int ab = NA == 2 ? (it & 1) : 0;
+      const uint32_t a_par = NA == 2 ? ((((uint32_t)it >> 1) & 1u) ^ 1u) : (((uint32_t)it & 1u) ^ 1u);
+      uint8_t* a_tile = a_smem + ab * KB1 * A_KBLOCK_BYTES;
+      if (warp == 4) { MP_TIMED(12, mbar_wait(&sh->in_full[s], ((uint32_t)it >> 1) & 1u)); MP_TIMED(13, mbar_wait(&sh->a_empty[ab], a_par)); }
+      else { mbar_wait(&sh->in_full[s], ((uint32_t)it >> 1) & 1u); mbar_wait(&sh->a_empty[ab], a_par); }
       const long long t_ln0 = SWN_MLP_PROFILE ? clock64() : 0;
       // one thread per row (the staging rows are padded to an odd number of 16-byte chunks, so this is bank
       // conflict free): no shuffles, long independent instruction streams.  Shifted one-pass moments.
@@ -353,10 +362,10 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mlp_persist_kernel(const MlpPar
           pk[0] = pack_op(y[0], y[1]); pk[1] = pack_op(y[2], y[3]);
           pk[2] = pack_op(y[4], y[5]); pk[3] = pack_op(y[6], y[7]);
         }
-        *reinterpret_cast<uint4*>(a_smem + (k >> 6) * A_KBLOCK_BYTES + sw128_offset(row, k & 63)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(a_tile + (k >> 6) * A_KBLOCK_BYTES + sw128_offset(row, k & 63)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
       fence_proxy_async();
-      mbar_arrive_warp(&sh->a_full[0]);
+      mbar_arrive_warp(&sh->a_full[ab]);
 #if SWN_MLP_PROFILE
       if (p.phase_cycles && warp == 4 && lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.phase_cycles + 14), (unsigned long long)(clock64() - t_ln0));
 #endif
@@ -529,7 +538,7 @@ int launch_mlp_persist(MlpParams p, int num_sms, cudaStream_t stream) {
   const int chunks = C / 4;
   p.row_stride = direct ? 0 : (chunks + ((chunks & 1) ? 0 : 1)) * 16;
   const int stage_bytes = (p.HC > p.TR ? p.HC : p.TR) * 128;
-  const int fixed = 1024 + ((direct ? 2 : 1) * KB1 + 2 * nkk) * A_KBLOCK_BYTES + 2 * TILE_M * p.row_stride + (4 * C + 3 * C16) * 4 +
+  const int fixed = 1024 + (((direct || SWN_MP_NA2) ? 2 : 1) * KB1 + 2 * nkk) * A_KBLOCK_BYTES + 2 * TILE_M * p.row_stride + (4 * C + 3 * C16) * 4 +
                     (int)sizeof(MpSmem) + 64 + (direct ? 8 * EPI_SCRATCH_BYTES + 16 : 0);
   int stages = (232448 - fixed) / stage_bytes;
   if (stages > 6) stages = 6;
