@@ -37,7 +37,7 @@ FUSED_WHOLE = {(12, 3), (24, 3), (48, 3), (48, 6)}    # (C, heads) instances of 
 FUSED_ATTN = {(96, 3), (96, 6)}                       # instances of swin_attn_stream_kernel (attention half)
 # (C, heads) that run one warp per window on mma.sync register fragments (csrc/swin_warp.cu) instead of swin_fused_kernel;
 # SWN_WARP_BLOCK=0 keeps the tcgen05 block kernel for A/B measurements
-WARP_BLOCK = {(12, 3), (24, 3)} if os.environ.get("SWN_WARP_BLOCK", "1") != "0" else set()
+WARP_BLOCK = {(12, 3), (24, 3), (48, 3), (48, 6)} if os.environ.get("SWN_WARP_BLOCK", "1") != "0" else set()
 WARP_LAYER = os.environ.get("SWN_WARP_LAYER", "1") != "0"    # all blocks of such a BasicLayer in one launch
 
 
@@ -289,7 +289,7 @@ class BasicLayer(nn.Module):
             for blk in self.blocks:
                 x = blk(x, resolution)
             return x
-        if (FUSED_BLOCK and WARP_LAYER and 1 <= len(self.blocks) <= 4 and x.shape[-1] == self.dim
+        if (FUSED_BLOCK and WARP_LAYER and 1 <= len(self.blocks) <= (4 if self.dim < 48 else 3) and x.shape[-1] == self.dim
                 and all((b.dim, b.num_heads) in WARP_BLOCK and b.shift_size == 0 for b in self.blocks)):
             # C = 12 / 24: every block of the layer uses the same (unshifted) window partition -> ONE launch carries the rows
             # of a window through all blocks in registers (csrc/swin_warp.cu)

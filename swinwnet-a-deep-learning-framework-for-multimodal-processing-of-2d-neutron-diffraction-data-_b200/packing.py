@@ -208,18 +208,22 @@ def mma_a_fragments(Wm: torch.Tensor) -> torch.Tensor:
 
 def pack_warp_block(n1w, n1b, Wqkv, bqkv, table, Wproj, bproj, n2w, n2b, W1, b1, W2, b2, num_heads: int):
     """Parameters of one SwinTransformerBlock (nn.Module layouts) -> (Wpk 16-bit flat, fpk fp32 flat) for
-    csrc/swin_warp.cu (C = 12 / 24, 3 heads).
+    csrc/swin_warp.cu (C = 12 / 24 / 48 with 3 heads, C = 48 with 6).
 
     Wpk = mma.sync fragments of [Wq | Wk | Wv (as A operand: v is produced transposed) | Wproj | W1 | W2], every matrix
     zero-padded to whole 8 / 16 tiles.  Folds done here in fp32: LayerNorm gamma into the columns of the following
-    weight; biases as two extra k columns — column C multiplies a constant 1 (the plain bias), column C+1 multiplies 1
-    for real tokens and 0 for zero-padded window tokens (W beta: the padded tokens of the reference are zeros AFTER
-    norm1, SwinWNet.py:242,254); head_dim^-0.5 log2(e) into q, log2(e) into the relative-position bias.
-    fpk = [b2 (K16) | bias fragments (nH * 1024)]."""
+    weight; head_dim^-0.5 log2(e) into q, log2(e) into the relative-position bias.  Biases:
+      * C = 12 / 24 (spare k columns behind the channels): two extra k columns — column C multiplies a constant 1 (the
+        plain bias), column C+1 multiplies 1 for real tokens and 0 for zero-padded window tokens (W beta: the padded tokens
+        of the reference are zeros AFTER norm1, SwinWNet.py:242,254);
+      * C = 48 (48 = 3 x 16, no spare column): fp32 vectors that initialise the accumulators — bq' bk' bv' (beta folded in,
+        real tokens), bq bk bv (zero-padded tokens), bproj, b1' — appended to fpk.
+    fpk = [b2 (K16) | bias fragments (nH * 1024) | (C = 48:) the 11 C bias floats]."""
     C = Wqkv.shape[1]
-    if num_heads != 3 or C not in (12, 24):
-        raise ValueError(f"pack_warp_block: C={C}, num_heads={num_heads} not supported (12 / 24 channels, 3 heads)")
+    if (C, num_heads) not in ((12, 3), (24, 3), (48, 3), (48, 6)):
+        raise ValueError(f"pack_warp_block: C={C}, num_heads={num_heads} not supported (12/3, 24/3, 48/3, 48/6)")
     K16, KT, NJ = warp_block_geometry(C)
+    biascol = K16 >= C + 2
     dev = Wqkv.device
     LOG2E = 1.4426950408889634
     qs = (C // num_heads) ** -0.5 * LOG2E
@@ -229,12 +233,13 @@ def pack_warp_block(n1w, n1b, Wqkv, bqkv, table, Wproj, bproj, n2w, n2b, W1, b1,
         z = torch.zeros(rows, K16, device=dev)
         n = Wm.shape[0]
         z[:n, :C] = Wm if gamma is None else Wm * gamma[None, :]
-        z[:n, C] = b
-        if beta is not None:
-            if split_beta:
-                z[:n, C + 1] = Wm @ beta
-            else:
-                z[:n, C] += Wm @ beta
+        if biascol:
+            z[:n, C] = b
+            if beta is not None:
+                if split_beta:
+                    z[:n, C + 1] = Wm @ beta
+                else:
+                    z[:n, C] += Wm @ beta
         return z
 
     g1, be1, g2, be2 = f(n1w), f(n1b), f(n2w), f(n2b)
@@ -252,7 +257,10 @@ def pack_warp_block(n1w, n1b, Wqkv, bqkv, table, Wproj, bproj, n2w, n2b, W1, b1,
     Wpk = Wpk.to(dt).contiguous()
     b2p = torch.zeros(K16, device=dev)
     b2p[:C] = f(b2)
-    fpk = torch.cat([b2p, rel_pos_bias_fragments(f(table), LOG2E).reshape(-1)]).contiguous()
+    fparts = [b2p, rel_pos_bias_fragments(f(table), LOG2E).reshape(-1)]
+    if not biascol:
+        fparts += [bq + Wq @ be1, bk + Wk @ be1, bv + Wv @ be1, bq, bk, bv, f(bproj), f(b1) + f(W1) @ be2]
+    fpk = torch.cat(fparts).contiguous()
     return Wpk, fpk
 
 

@@ -320,11 +320,15 @@ def test_swin_block_fused(C, nH, B, H, W, do_mlp):
 
 @pytest.mark.parametrize("C,B,H,W", [
     (12, 2, 10, 15), (12, 2, 13, 9), (12, 1, 40, 65), (12, 1, 5, 5), (12, 1, 3, 4), (12, 1, 240, 245), (12, 3, 100, 190),
-    (24, 2, 10, 15), (24, 1, 32, 61), (24, 1, 5, 5), (24, 1, 2, 7), (24, 1, 180, 175), (24, 2, 125, 240)])
+    (24, 2, 10, 15), (24, 1, 32, 61), (24, 1, 5, 5), (24, 1, 2, 7), (24, 1, 180, 175), (24, 2, 125, 240),
+    (48, 2, 10, 15), (48, 1, 13, 9), (48, 1, 3, 4), (48, 3, 25, 40), (48, 2, 100, 101), (48, 2, 125, 240),
+    (48.6, 1, 12, 23), (48.6, 2, 63, 121)])
 def test_swin_block_warp(C, B, H, W):
     """one-warp-per-window block kernel (csrc/swin_warp.cu) against the oracle block: window padding (H, W not multiples
-    of 5: zero tokens AFTER norm1 that still act as keys), images smaller than a window, many windows per warp"""
-    nH = 3
+    of 5: zero tokens AFTER norm1 that still act as keys), images smaller than a window, many windows per warp;
+    C = 48.6 stands for 48 channels with 6 heads"""
+    nH = 6 if C == 48.6 else 3
+    C = int(C)
     x = rnd(B, H * W, C, seed=1) * 1.5 + 0.2
     sd, order = _block_sd(C, nH)
     ref = O.swin_block(sd, "", x, (H, W), nH, 0)
@@ -343,7 +347,7 @@ def test_swin_block_warp(C, B, H, W):
 
 
 @pytest.mark.parametrize("C,B,H,W,depth", [(12, 2, 13, 9, 2), (12, 1, 100, 190, 2), (24, 1, 32, 61, 2), (24, 2, 125, 240, 3),
-                                           (12, 1, 40, 65, 4)])
+                                           (12, 1, 40, 65, 4), (48, 2, 13, 9, 2), (48, 2, 125, 240, 2), (48, 1, 32, 61, 3)])
 def test_swin_block_warp_layer(C, B, H, W, depth):
     """`depth` consecutive blocks (different weights) in one launch == the oracle blocks applied one after the other"""
     nH = 3
@@ -361,8 +365,11 @@ def test_swin_block_warp_layer(C, B, H, W, depth):
     ops.swin_block_warp(xd, out, B, H, W, C, nH, 1e-5, torch.cat(Wl), torch.cat(fl), depth)
     torch.cuda.synchronize()
     assert relerr(out, ref) <= TOL_BF16 / 4 * depth ** 0.5
-    with pytest.raises(RuntimeError, match="depth"):
-        ops.swin_block_warp(xd, out, B, H, W, C, nH, 1e-5, torch.cat(Wl), torch.cat(fl), 5)
+    with pytest.raises(RuntimeError, match="depth" if C < 48 else "depth|shared memory"):
+        ops.swin_block_warp(xd, out, B, H, W, C, nH, 1e-5, torch.cat(Wl + Wl)[:5 * Wl[0].numel()], torch.cat(fl + fl)[:5 * fl[0].numel()], 5)
+    if C == 48 and depth == 3:      # four blocks of C = 48 do not fit in shared memory: loud error, nothing launched
+        with pytest.raises(RuntimeError, match="shared memory"):
+            ops.swin_block_warp(xd, out, B, H, W, C, nH, 1e-5, torch.cat(Wl + Wl[:1]), torch.cat(fl + fl[:1]), 4)
 
 
 @pytest.mark.parametrize("nH,B,H,W", [(3, 2, 10, 15), (6, 1, 13, 9), (3, 1, 63, 120), (6, 2, 100, 101)])

@@ -278,20 +278,23 @@ def test_warp_block_packing_replays_the_kernel_dataflow():
             out[:, i] += Cm[g + 8 * (i // 2), 2 * t + i % 2]
         return out
 
-    for C in (12, 24):
-        nH, hd = 3, C // 3
+    for C, nH in ((12, 3), (24, 3), (48, 3), (48, 6)):
+        hd = C // nH
         K16, KT, NJ = packing.warp_block_geometry(C)
+        biascol = K16 >= C + 2
         shp = [(C,), (C,), (3 * C, C), (3 * C,), (81, nH), (C, C), (C,), (C,), (C,), (4 * C, C), (4 * C,), (C, 4 * C), (C,)]
         prm = [torch.randn(*s) * (s[-1] ** -0.5 if len(s) == 2 else 0.2) + (1.0 if i in (0, 7) else 0.0) for i, s in enumerate(shp)]
         n1w, n1b, Wqkv, bqkv, table, Wproj, bproj, n2w, n2b, W1, b1, W2, b2 = prm
         Wpk, fpk = packing.pack_warp_block(*prm, nH)
         Wpk = Wpk.float()
         sizes = [KT * NJ * 128, KT * NJ * 128, KT * KT * 256, KT * NJ * 128, KT * (C // 2) * 128, (C // 4) * NJ * 128]
-        assert Wpk.numel() == sum(sizes) and fpk.numel() == K16 + nH * 1024      # WbGeom::W_ELEMS / F_ELEMS
+        assert Wpk.numel() == sum(sizes) and fpk.numel() == K16 + nH * 1024 + (0 if biascol else 11 * C)   # WbGeom::W_ELEMS / F_ELEMS
+        xb = fpk[K16 + nH * 1024:]
+        bqf, bkf, bvf, bqp, bkp, bvp, bpj, b1f = (torch.split(xb, [C] * 7 + [4 * C]) if not biascol else [None] * 8)
         Q, K, V, P, F1, F2 = torch.split(Wpk, sizes)
         Q, K, P = [m.view(KT, NJ, 32, 4) for m in (Q, K, P)]
         V, F1, F2 = V.view(KT, KT, 32, 8), F1.view(KT, C // 2, 32, 4), F2.view(C // 4, NJ, 32, 4)
-        bias_frag = fpk[K16:].view(nH, 2, 4, 32, 4)
+        bias_frag = fpk[K16:K16 + nH * 1024].view(nH, 2, 4, 32, 4)
         # a 4 x 5 image: one window, its fifth row is zero padding (AFTER norm1) — oracle reference
         H, W = 4, 5
         x = torch.randn(1, H * W, C) * 1.5 + 0.3
@@ -326,17 +329,29 @@ def test_warp_block_packing_replays_the_kernel_dataflow():
             xn = (m[:, :C] - mu) * torch.rsqrt(m[:, :C].var(-1, unbiased=False, keepdim=True) + 1e-5)
             z = torch.zeros(32, K16)
             z[:, :C] = xn * (real[:, None] if first else 1.0)
-            z[:, C] = 1.0
-            z[:, C + 1] = real.float() if first else 0.0
+            if biascol:
+                z[:, C] = 1.0
+                z[:, C + 1] = real.float() if first else 0.0
             return a_frags(to_frag(z))
+
+        def rowbias(fold, plain, ncols):      # accumulator start without bias columns: per row the folded / the plain bias
+            m = torch.zeros(32, ncols)
+            m[:, :C] = torch.where(real[:, None], fold[None, :], plain[None, :])
+            return to_frag_n(m, ncols)
+
+        def to_frag_n(m, ncols):
+            return [[torch.stack([m[16 * mt + g + 8 * (i // 2), 8 * j + 2 * t + i % 2] for i in range(4)], 1)
+                     for j in range(ncols // 8)] for mt in range(2)]
 
         a1 = layer_norm_frags(rows, True)
         zero = torch.zeros(32, 4)
         q = [[None] * NJ for _ in range(2)]
         k = [[None] * NJ for _ in range(2)]
+        q0 = rowbias(bqf, bqp, NJ * 8) if not biascol else None
+        k0 = rowbias(bkf, bkp, NJ * 8) if not biascol else None
         for n in range(NJ):
             for mt in range(2):
-                qc, kc = zero, zero
+                qc, kc = (zero, zero) if biascol else (q0[mt][n], k0[mt][n])
                 for kt in range(KT):
                     qc, kc = mma(a1[mt][kt], Q[kt, n], qc), mma(a1[mt][kt], K[kt, n], kc)
                 q[mt][n], k[mt][n] = qc, kc
@@ -350,6 +365,10 @@ def test_warp_block_packing_replays_the_kernel_dataflow():
         for mv in range(KT):
             for nt in range(4):
                 vc = zero
+                if not biascol:     # rows = channels 16 mv + g (+8), columns = tokens 8 nt + 2t (+1)
+                    tokreal = torch.stack([real[8 * nt + 2 * t + i % 2] for i in range(4)], 1)
+                    ch = torch.stack([16 * mv + g + 8 * (i // 2) for i in range(4)], 1)
+                    vc = torch.where(tokreal, bvf[ch], bvp[ch])
                 for kt in range(KT):
                     af = a1[nt // 2][kt]
                     vc = mma(V[mv, kt], torch.cat([af[:, 2 * (nt % 2):2 * (nt % 2) + 2], af[:, 4 + 2 * (nt % 2):6 + 2 * (nt % 2)]], 1), vc)
@@ -368,9 +387,13 @@ def test_warp_block_packing_replays_the_kernel_dataflow():
             s = qm[:, h * hd:(h + 1) * hd] @ km[:, h * hd:(h + 1) * hd].t() + bias
             pr = torch.exp2(s - s.max(-1, keepdim=True).values)
             o[:, h * hd:(h + 1) * hd] = (pr @ vT[h * hd:(h + 1) * hd].t()) / pr.sum(-1, keepdim=True)
-        o[:, C] = 1.0
+        if biascol:
+            o[:, C] = 1.0
         ao = a_frags(to_frag(o))
-        x1 = to_frag(rows)
+        rows_b = rows.clone()
+        if not biascol:
+            rows_b[:, :C] += bpj
+        x1 = to_frag(rows_b)
         for mt in range(2):
             for j in range(NJ):
                 for kt in range(KT):
@@ -382,6 +405,9 @@ def test_warp_block_packing_replays_the_kernel_dataflow():
         for u in range(C // 4):
             for mt in range(2):
                 h0, h1 = zero, zero
+                if not biascol:
+                    h0 = torch.stack([b1f[16 * u + 2 * t + i % 2] for i in range(4)], 1)
+                    h1 = torch.stack([b1f[16 * u + 8 + 2 * t + i % 2] for i in range(4)], 1)
                 for kt in range(KT):
                     h0, h1 = mma(a2[mt][kt], F1[kt, 2 * u], h0), mma(a2[mt][kt], F1[kt, 2 * u + 1], h1)
                 ge = lambda v: torch.nn.functional.gelu(v)

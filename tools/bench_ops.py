@@ -72,7 +72,7 @@ for (L, C, nH, H, W) in SHAPES:
         for do_mlp in (True, False):
             ms = timeit(lambda: ops.swin_block_fused(x, out, B, H, W, C, nH, 1e-5, Wpk, fpk, do_mlp))
             report("fblk" if do_mlp else "fattn", M, C, ms, M * C * 8, ((24.0 if do_mlp else 8.0) * C * C + 100.0 * C) * M)
-    if "warp" in a.ops and C in (12, 24):
+    if "warp" in a.ops and C in (12, 24, 48):
         shp = [(C,), (C,), (3 * C, C), (3 * C,), (81, nH), (C, C), (C,), (C,), (C,), (4 * C, C), (4 * C,), (C, 4 * C), (C,)]
         params = [torch.randn(*s, device=DEV) * 0.1 for s in shp]
         Wpk, fpk = packing.pack_warp_block(*params, nH)
