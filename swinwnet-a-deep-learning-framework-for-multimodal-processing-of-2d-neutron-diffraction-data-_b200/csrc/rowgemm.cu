@@ -323,6 +323,43 @@ __global__ void __launch_bounds__(RG_THREADS, 1) rowgemm_kernel(const RowGemmPar
         tc_fence_before();
         mbar_arrive_warp(&sh->tmem_empty[buf]);
       }
+    } else if constexpr (EP == 3) {   // 16-bit output in TRANSPOSED ownership: 8 rows x 32 contiguous bytes per store instruction
+      uint8_t* scr = reinterpret_cast<uint8_t*>(bias_s + ((p.nchunks * p.NT + 3) & ~3)) + (warp - 2) * EPI_SCRATCH_BYTES;
+      const int cq = (lane & 3) * 4, rq = lg * 32 + (lane >> 2);
+      for (int n = 0; n < p.nchunks; ++n) {
+        const int buf = n & 1;
+        mbar_wait(&sh->tmem_full[buf], ((uint32_t)n >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t t_row = lane_addr + (uint32_t)(buf * nt32);
+        const float* bias = p.bias ? bias_s + n * p.NT : nullptr;
+        const long long col0 = (long long)n * p.n_valid;
+        for (int jb = half; jb < nblk; jb += 2) {
+          tmem_ld16(t_row + jb * 16, v);
+          tmem_ld_wait();
+          const int c0 = jb * 16;
+          if (bias) {
+#pragma unroll
+            for (int j4 = 0; j4 < 16; j4 += 4) {
+              const float4 bv = *reinterpret_cast<const float4*>(bias + c0 + j4);
+              v[j4] += bv.x; v[j4 + 1] += bv.y; v[j4 + 2] += bv.z; v[j4 + 3] += bv.w;
+            }
+          }
+          epi_scatter16(scr, v, lane);
+          const int c = c0 + cq;
+          if (c < p.n_valid) {
+#pragma unroll
+            for (int ps = 0; ps < 4; ++ps) {
+              const long long mm = m0 + rq + ps * 8;
+              if (mm >= p.M) continue;
+              const float4 y = epi_gather4(scr, ps, lane);
+              *reinterpret_cast<uint2*>(reinterpret_cast<op_t*>(p.out) + mm * p.ldo + col0 + c) = make_uint2(pack_op(y.x, y.y), pack_op(y.z, y.w));
+            }
+          }
+          __syncwarp();
+        }
+        tc_fence_before();
+        mbar_arrive_warp(&sh->tmem_empty[buf]);
+      }
     } else {
       const bool vec8 = (p.ldo % 8 == 0) && (p.n_valid % 8 == 0);
       for (int n = 0; n < p.nchunks; ++n) {
@@ -407,8 +444,14 @@ int launch_rowgemm(RowGemmParams p, cudaStream_t stream) {
   // 0.262 -> 0.176 ms) and loses on narrow ones (48 columns: 0.54 -> 0.82 ms: its 16 KB of scratch costs co-resident CTAs).
   p.res_stride = (p.e_mode == E_F32 && p.res != nullptr && p.nchunks * p.n_valid >= 128 && p.ldres % 4 == 0) ? 1 : 0;
   // + bias staged in shared memory, + 2 KB transposition scratch per epilogue warp for the transposed fp32 epilogue
+#ifndef SWN_RG_T16
+#define SWN_RG_T16 1
+#endif
+  // the same transposition for 16-bit outputs: pays at K = 384 (qkv: 0.293 -> 0.275 ms, 0.098 -> 0.094), loses at K = 192 (0.444 ->
+  // 0.506 ms: the 16 KB of scratch take two of the five weight-ring stages of the two co-resident CTAs)
+  const bool t16 = SWN_RG_T16 && p.e_mode == E_BF16 && p.K > 256 && p.nchunks * p.n_valid >= 128 && p.ldo % 4 == 0;
   const int fixed = 1024 + a_bytes + (int)sizeof(RgSmem) + 64 + p.nchunks * p.NT * 4 + 16 +
-                    (p.res_stride ? (RG_WARPS - 2) * EPI_SCRATCH_BYTES : 0);
+                    ((p.res_stride || t16) ? (RG_WARPS - 2) * EPI_SCRATCH_BYTES : 0);
   // aim for >= 2 co-resident CTAs per SM (smem <= ~113 KB) when that still leaves >= 2 ring stages
   int stages = (113 * 1024 - fixed) / stage_bytes;
   if (stages < 2) stages = (232448 - fixed) / stage_bytes;
@@ -426,9 +469,9 @@ int launch_rowgemm(RowGemmParams p, cudaStream_t stream) {
     SWN_CUDA(cudaGetLastError());
     return 0;
   };
-  const int ep = p.e_mode == E_EXPAND ? 1 : (p.res_stride ? 2 : 0);
+  const int ep = p.e_mode == E_EXPAND ? 1 : (p.res_stride ? 2 : (t16 ? 3 : 0));
 #define SWN_RG_DISPATCH(LPR_, KV_) \
-  return ep == 1 ? go(rowgemm_kernel<LPR_, KV_, 1>) : (ep == 2 ? go(rowgemm_kernel<LPR_, KV_, 2>) : go(rowgemm_kernel<LPR_, KV_, 0>))
+  return ep == 1 ? go(rowgemm_kernel<LPR_, KV_, 1>) : (ep == 2 ? go(rowgemm_kernel<LPR_, KV_, 2>) : (ep == 3 ? go(rowgemm_kernel<LPR_, KV_, 3>) : go(rowgemm_kernel<LPR_, KV_, 0>)))
   if (p.K <= 16) SWN_RG_DISPATCH(4, 1);
   if (p.K <= 32) SWN_RG_DISPATCH(8, 1);
   if (p.K <= 64) SWN_RG_DISPATCH(16, 1);
