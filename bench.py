@@ -356,6 +356,8 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":     # keeps NCCL's version banner off stdout (one JSON line)
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     man = json.load(open(os.path.join(ROOT, "tests", "golden", "manifest.json")))
