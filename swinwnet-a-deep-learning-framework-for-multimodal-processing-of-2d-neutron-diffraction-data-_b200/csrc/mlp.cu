@@ -4,7 +4,8 @@
 // One CTA (10 warps) owns 128 token rows.  LayerNorm(x) is written once to shared memory as the resident
 // bf16 A operand (all warps, see build_a_tile).  The 4C hidden dimension is processed in chunks of HC columns:
 //     GEMM1  Hacc[128 x HC]  = A[128 x C] * W1_j^T        (TMEM, double buffered)
-//     epilogue-1 (8 warps)   : +b1, exact GELU, -> bf16 swizzled smem tile Hs (double buffered)
+//     epilogue-1 (8 warps)   : +b1, GELU (tanh form with a fitted argument, packed half2: common.cuh::gelu_pack2; |d| <= 3e-5
+//                              against erf-GELU before the 16-bit rounding), -> 16-bit swizzled smem tile Hs (double buffered)
 //     GEMM2  Y[128 x C]     += Hs[128 x HC] * W2_j^T      (TMEM, resident across chunks)
 // so the 4C-wide hidden activation never leaves the SM.  GEMM1 of chunk j+1 is issued before GEMM2 of
 // chunk j, which keeps the tensor pipe busy while the epilogue warps run GELU on chunk j.  Weights are
