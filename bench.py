@@ -174,7 +174,7 @@ def library_bar(dev, batches=(8, 64), iters=3):
 FAMILIES = {
     "fused": "swn::swin_warp_block_kernel + swin_fused_kernel + swin_attn_stream_kernel (fused LN1+qkv+W-MSA+proj[+LN2+MLP], C<=96)",
     "mlp": "swn::mlp_kernel + mlp_persist_kernel (fused LN2+fc1+GELU+fc2+residual, C>=96)",
-    "rowgemm": "swn::rowgemm_kernel + rowgemm_persist_kernel (LN/merge/convert prologue + GEMM + bias/residual/expand epilogue)",
+    "rowgemm": "swn::rowgemm_kernel + rowgemm_persist_kernel + expand_warp_kernel (LN/merge/convert prologue + GEMM + bias/residual/expand epilogue)",
     "window_attn": "swn::window_attn_warp_kernel (+ window_attn_kernel for shift > 0) (W-MSA core on materialised qkv, C>=192)",
     "cross_attn": "swn::cross_attn_kernel (flash-style global MHA core)",
     "heads": "swn::patch_embed_kernel + conv_head_mma_kernel + bilinear_up_kernel",

@@ -16,7 +16,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SOURCES = ["api.cu", "rowgemm.cu", "rowgemm_persist.cu", "mlp.cu", "mlp_persist.cu", "window_attn.cu", "small_block.cu",
-           "swin_fused.cu", "swin_warp.cu", "cross_attn.cu", "elementwise.cu", "train_ops.cu"]
+           "swin_fused.cu", "swin_warp.cu", "expand_warp.cu", "cross_attn.cu", "elementwise.cu", "train_ops.cu"]
 HEADERS = ["common.cuh", "kernels.h", os.path.join("..", "..", "include", "swinwnet_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

@@ -107,7 +107,9 @@ int swn_rowgemm(const swn_rowgemm_args* a, void* stream) {
   SWN_CHECK(p.M > 0 && p.K > 0 && p.K % 4 == 0 && p.NT >= 16 && p.NT <= 256 && p.NT % 16 == 0 && p.n_valid > 0 &&
                 p.n_valid <= p.NT && p.n_valid % 4 == 0 && p.nchunks >= 1 && p.ldo % 4 == 0,
             "rowgemm: bad shape arguments");
-  const int rc = launch_rowgemm_persist(p, num_sms(), reinterpret_cast<cudaStream_t>(stream));
+  int rc = launch_expand_warp(p, num_sms(), reinterpret_cast<cudaStream_t>(stream));
+  if (rc >= 0) return rc;
+  rc = launch_rowgemm_persist(p, num_sms(), reinterpret_cast<cudaStream_t>(stream));
   if (rc >= 0) return rc;
   return launch_rowgemm(p, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -39,6 +39,8 @@ struct RowGemmParams {
   int res_stride;             // residual staging row stride (bytes), 0 = residual read from global
 };
 int launch_rowgemm(RowGemmParams p, cudaStream_t stream);
+// warp-level (mma.sync) PatchExpanding for K <= 48 (expand_warp.cu); returns -1 (no error) when the shape does not qualify
+int launch_expand_warp(RowGemmParams p, int num_sms, cudaStream_t stream);
 // persistent TMA-staged variant for narrow layers; returns -1 (no error) when the shape does not qualify
 int launch_rowgemm_persist(RowGemmParams p, int num_sms, cudaStream_t stream);
 

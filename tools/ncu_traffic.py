@@ -16,7 +16,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 FAMILY = [("swin_warp_block_kernel", "fused"), ("swin_fused_kernel", "fused"), ("swin_attn_stream_kernel", "fused"), ("swin_block_small", "fused"),
-          ("mlp_persist_kernel", "mlp"), ("mlp_kernel", "mlp"), ("rowgemm", "rowgemm"), ("window_attn", "window_attn"),
+          ("mlp_persist_kernel", "mlp"), ("mlp_kernel", "mlp"), ("rowgemm", "rowgemm"), ("expand_warp", "rowgemm"), ("window_attn", "window_attn"),
           ("cross_attn", "cross_attn"), ("patch_embed", "heads"), ("conv_head", "heads"), ("bilinear", "heads")]
 
 
