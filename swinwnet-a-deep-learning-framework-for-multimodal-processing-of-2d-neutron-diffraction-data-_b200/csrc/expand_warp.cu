@@ -69,7 +69,8 @@ __global__ void __launch_bounds__(XW_THREADS, SWN_XW_MINB) expand_warp_kernel(co
       obase[s] = -1;
       oy[s] = ox[s] = 0;
       if (ok) {
-        const int eb = (int)(m / hw), rem = (int)(m - (long long)eb * hw);
+        const int mi = (int)m;          // M < 2^31 (checked by the launcher): 32-bit divisions
+        const int eb = mi / hw, rem = mi - eb * hw;
         const int eh = rem / p.xW, ew = rem - eh * p.xW;
         oy[s] = 2 * eh;
         ox[s] = 2 * ew;
@@ -112,7 +113,8 @@ __global__ void __launch_bounds__(XW_THREADS, SWN_XW_MINB) expand_warp_kernel(co
           q = fmaf(d0, d0, q);
           q = fmaf(d1, d1, q);
         }
-        const float rstd = rsqrtf(xw_quad_sum(q) * inv_n + p.ln_eps);
+        float rstd;
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rstd) : "f"(xw_quad_sum(q) * inv_n + p.ln_eps));
         const int yy = oy[s] + (n >> 1), xx = ox[s] + (n & 1);
         if (obase[s] >= 0 && yy < p.xHs && xx < p.xWs) {
           float* orow = out + (obase[s] + (long long)yy * p.xWs + xx) * p.ldo;
