@@ -355,6 +355,11 @@ __device__ __forceinline__ void mma_f16(float* c, const uint32_t* a, uint32_t b0
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// GELU of the conv heads' hidden layer: the tanh form with the fitted argument (|d| <= 3e-5 against erf-GELU, common.cuh) — the
+// Abramowitz-Stegun erf was 21 % of the recon head's instructions.  -DSWN_HEAD_GELU=gelu_erf restores it.
+#ifndef SWN_HEAD_GELU
+#define SWN_HEAD_GELU gelu_fast
+#endif
 template <int CI, int CM>
 __global__ void __launch_bounds__(256) conv_head_h_kernel(const float* __restrict__ tok, const float* __restrict__ w1,
                                                           const float* __restrict__ b1, const float* __restrict__ w2,
@@ -392,13 +397,13 @@ __global__ void __launch_bounds__(256) conv_head_h_kernel(const float* __restric
     for (int i = tid; i < (TH + 2) * (TW + 2); i += 256)
       for (int c = CI; c < K16; c += 2) *reinterpret_cast<uint32_t*>(in_s + i * PSB + c * 2) = 0u;
   const int tiles_x = (Wout + TW - 1) / TW, tiles_y = (Hout + TH - 1) / TH;
-  const long long n_tiles = (long long)B * tiles_y * tiles_x;
+  const int n_tiles = B * tiles_y * tiles_x;      // < 2^31 (checked by the launcher): 32-bit tile arithmetic
   constexpr int NLD = ((TH + 2) * (TW + 2) * (CI / 4) + 255) / 256;
   constexpr bool PREFETCH = NLD <= 4;
   float4 pre[PREFETCH ? NLD : 1];
-  auto load_tile = [&](long long tile, float4* dst) {
-    const int b = (int)(tile / (tiles_y * tiles_x));
-    const int tr = (int)(tile - (long long)b * tiles_y * tiles_x);
+  auto load_tile = [&](int tile, float4* dst) {
+    const int b = tile / (tiles_y * tiles_x);
+    const int tr = tile - b * tiles_y * tiles_x;
     const int y0 = (tr / tiles_x) * TH, x0 = (tr % tiles_x) * TW;
 #pragma unroll
     for (int q = 0; q < NLD; ++q) {
@@ -410,10 +415,10 @@ __global__ void __launch_bounds__(256) conv_head_h_kernel(const float* __restric
         dst[q] = __ldg(reinterpret_cast<const float4*>(tok + (((long long)b * Hh + yy) * Wh + xx) * CI + c4 * 4));
     }
   };
-  if constexpr (PREFETCH) if ((long long)blockIdx.x < n_tiles) load_tile(blockIdx.x, pre);
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int b = (int)(tile / (tiles_y * tiles_x));
-    const int tr = (int)(tile - (long long)b * tiles_y * tiles_x);
+  if constexpr (PREFETCH) if ((int)blockIdx.x < n_tiles) load_tile((int)blockIdx.x, pre);
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int b = tile / (tiles_y * tiles_x);
+    const int tr = tile - b * tiles_y * tiles_x;
     const int y0 = (tr / tiles_x) * TH, x0 = (tr % tiles_x) * TW;
     __syncthreads();   // previous tile fully consumed (and the weights staged, first time round)
     if constexpr (PREFETCH) {
@@ -425,7 +430,7 @@ __global__ void __launch_bounds__(256) conv_head_h_kernel(const float* __restric
           *reinterpret_cast<uint2*>(in_s + pix * PSB + c4 * 8) = make_uint2(pack_half2_sat(pre[q].x, pre[q].y), pack_half2_sat(pre[q].z, pre[q].w));
         }
       }
-      if (tile + gridDim.x < n_tiles) load_tile(tile + gridDim.x, pre);
+      if (tile + (int)gridDim.x < n_tiles) load_tile(tile + (int)gridDim.x, pre);
     } else {
       for (int i = tid; i < (TH + 2) * (TW + 2) * (CI / 4); i += 256) {
         const int c4 = i % (CI / 4), pix = i / (CI / 4);
@@ -476,7 +481,7 @@ __global__ void __launch_bounds__(256) conv_head_h_kernel(const float* __restric
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int ch = n * 8 + 2 * t4 + (e & 1);
-          const float h = gelu_erf(acc[m][n][e] + b1_s[ch]);
+          const float h = SWN_HEAD_GELU(acc[m][n][e] + b1_s[ch]);
           o[e >> 1][0] = fmaf(h, w2_s[ch], o[e >> 1][0]);
           o[e >> 1][1] = fmaf(h, w2_s[NT * 8 + ch], o[e >> 1][1]);
         }
