@@ -186,6 +186,23 @@ def test_run_host_pipelined_copies_match_device_call(wnet_em):
         inf.host_done.synchronize()
         assert out.is_pinned() and out.shape == ref.shape
         assert torch.equal(out, ref.cpu())
+    # full chunks replay a captured CUDA graph (host_graph, default): replays of the same graph on new data, the eager
+    # host path, and the bound on the number of graphs kept
+    assert 1 <= len(inf._graphs) <= inf.MAX_GRAPHS
+    x2 = O.synthetic_diffractions(4, seed=34, H=60, W=80, two_channel=False)
+    ref2 = inf(x2.to(DEV)).clone()
+    out2 = inf.run_host(x2.pin_memory(), chunk=2)
+    inf.host_done.synchronize()
+    assert torch.equal(out2, ref2.cpu())
+    assert torch.equal(inf.images_masked_hr, ref2[2:])            # cached stage attributes: those of the last chunk
+    eager = S.SwinWNetInference(wnet_em, DEV, host_graph=False)
+    out3 = eager.run_host(x2.pin_memory(), chunk=2)
+    eager.host_done.synchronize()
+    assert torch.equal(out3, out2) and not eager._graphs
+    for chunk in (1, 3, 4):
+        inf.run_host(x2.pin_memory(), chunk=chunk)
+    inf.host_done.synchronize()
+    assert len(inf._graphs) == inf.MAX_GRAPHS
 
 
 def test_state_dict_round_trip_and_repack(manifest):
