@@ -95,6 +95,11 @@ int swn_set_phase_profile(void* device_buffer);
 /* 5x5 (shifted-)window attention core on token-ordered qkv (SwinWNet.py:86-149,183-206,246-272). */
 int swn_window_attention(const void* qkv_bf16, void* out_bf16, const float* qkv_bias, const float* rpb_table,
                          int B, int H, int W, int C, int num_heads, int shift, void* stream);
+/* The same for shift 0 with the relative-position bias of every head already expanded to the [nH][2][4][32][4] fp32
+ * accumulator-fragment images of the kernel (log2 domain, packing.py::rel_pos_bias_fragments): the kernel copies 4 KB per
+ * head instead of rebuilding the images from the [81, nH] table in every CTA (a third of the launch at 16x30 tokens). */
+int swn_window_attention_frags(const void* qkv_bf16, void* out_bf16, const float* qkv_bias, const float* rpb_table,
+                               const float* bias_frags, int B, int H, int W, int C, int num_heads, void* stream);
 
 /* flash-style global cross attention core, heads of 64 or 128 channels (SwinWNet.py:782). */
 int swn_cross_attention(const void* q_bf16, const void* kv_bf16, void* out_bf16, int B, int Lq, int Lk, int C,

@@ -46,6 +46,8 @@ SIGNATURES = {
     "swn_set_phase_profile": (c_int, [c_void_p]),
     "swn_window_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                      c_void_p]),
+    "swn_window_attention_frags": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                           c_void_p]),
     "swn_cross_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "swn_patch_embed": (c_int, [c_void_p] * 6 + [c_int] * 7 + [c_void_p]),
     "swn_seg_head": (c_int, [c_void_p] * 7 + [c_int] * 6 + [c_void_p]),

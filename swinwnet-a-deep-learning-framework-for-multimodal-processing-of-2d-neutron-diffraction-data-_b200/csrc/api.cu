@@ -168,7 +168,16 @@ int swn_window_attention(const void* qkv, void* out, const float* qkv_bias, cons
   SWN_CHECK(qkv && out && qkv_bias && rpb_table, "window_attention: null pointer");
   SWN_CHECK(B > 0 && H > 0 && W > 0 && C % 4 == 0 && num_heads > 0 && shift >= 0, "window_attention: bad sizes");
   WinAttnParams p{reinterpret_cast<const op_t*>(qkv), reinterpret_cast<op_t*>(out), qkv_bias, rpb_table,
-                  B, H, W, C, num_heads, shift};
+                  B, H, W, C, num_heads, shift, nullptr};
+  return launch_window_attn(p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int swn_window_attention_frags(const void* qkv, void* out, const float* qkv_bias, const float* rpb_table, const float* bias_frags,
+                               int B, int H, int W, int C, int num_heads, void* stream) {
+  SWN_CHECK(qkv && out && qkv_bias && rpb_table && bias_frags, "window_attention_frags: null pointer");
+  SWN_CHECK(B > 0 && H > 0 && W > 0 && C % 4 == 0 && num_heads > 0, "window_attention_frags: bad sizes");
+  WinAttnParams p{reinterpret_cast<const op_t*>(qkv), reinterpret_cast<op_t*>(out), qkv_bias, rpb_table,
+                  B, H, W, C, num_heads, 0, bias_frags};
   return launch_window_attn(p, reinterpret_cast<cudaStream_t>(stream));
 }
 

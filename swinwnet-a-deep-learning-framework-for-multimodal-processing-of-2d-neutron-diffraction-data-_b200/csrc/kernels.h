@@ -72,6 +72,8 @@ struct WinAttnParams {
   const float* qkv_bias;     // [3C]: q/k/v of zero-padded tokens (pad happens after norm1)
   const float* rpb_table;    // [81, nH]
   int B, H, W, C, nH, shift;
+  const float* bias_frags;   // optional: [nH][2][4][32][4] bias images in accumulator order, log2 domain (packing.py::
+                             // rel_pos_bias_fragments); the warp kernel then copies them instead of building them per CTA
 };
 int launch_window_attn(WinAttnParams p, cudaStream_t stream);
 

@@ -281,13 +281,19 @@ __global__ void __launch_bounds__(WW_THREADS, 2) window_attn_warp_kernel(const W
   extern __shared__ __align__(16) uint8_t ww_smem[];
   float* bias_f = reinterpret_cast<float*>(ww_smem);           // [nH][2 mt][4 nt][32 lanes][4]
   const int C = p.C, nH = p.nH, C3 = 3 * p.C;
-  for (int i = threadIdx.x; i < nH * 1024; i += WW_THREADS) {
-    const int e = i & 3, ln = (i >> 2) & 31, tile = (i >> 7) & 7, h = i >> 10;
-    const int row = (tile >> 2) * 16 + (ln >> 2) + (e >> 1) * 8, key = (tile & 3) * 8 + (ln & 3) * 2 + (e & 1);
-    float v = 0.f;
-    if (key >= WN) v = -1e30f;                                  // key columns 25..31: padding of the mma tile
-    else if (row < WN) v = __ldg(p.rpb_table + ((row / WS - key / WS + WS - 1) * (2 * WS - 1) + (row % WS - key % WS + WS - 1)) * nH + h) * 1.4426950408889634f;
-    bias_f[i] = v;
+  if (p.bias_frags) {   // ready-made images (built once per block on the host side of the C ABI): 4 KB per head, vector copy
+    for (int i = threadIdx.x; i < nH * 256; i += WW_THREADS)
+      reinterpret_cast<float4*>(bias_f)[i] = __ldg(reinterpret_cast<const float4*>(p.bias_frags) + i);
+  } else {              // from the [81, nH] table: ~40 instructions per entry, 22 us per CTA at 24 heads — a third of the
+                        // whole launch at 16 x 30 tokens (measured), which is why the images can be passed in
+    for (int i = threadIdx.x; i < nH * 1024; i += WW_THREADS) {
+      const int e = i & 3, ln = (i >> 2) & 31, tile = (i >> 7) & 7, h = i >> 10;
+      const int row = (tile >> 2) * 16 + (ln >> 2) + (e >> 1) * 8, key = (tile & 3) * 8 + (ln & 3) * 2 + (e & 1);
+      float v = 0.f;
+      if (key >= WN) v = -1e30f;                                  // key columns 25..31: padding of the mma tile
+      else if (row < WN) v = __ldg(p.rpb_table + ((row / WS - key / WS + WS - 1) * (2 * WS - 1) + (row % WS - key % WS + WS - 1)) * nH + h) * 1.4426950408889634f;
+      bias_f[i] = v;
+    }
   }
   __syncthreads();
   const float4* bias4 = reinterpret_cast<const float4*>(bias_f);

@@ -164,6 +164,7 @@ class SwinTransformerBlock(nn.Module):
             for k, p in (("qkv_b", a.qkv.bias), ("b1", self.mlp[0].bias), ("n1w", self.norm1.weight), ("n1b", self.norm1.bias),
                          ("n2w", self.norm2.weight), ("n2b", self.norm2.bias), ("tab", a.relative_position_bias_table)):
                 d[k] = _f32(p)
+            d["tabfrag"] = packing.rel_pos_bias_fragments(d["tab"], 1.4426950408889634).reshape(-1).contiguous()
             return d
         return self._cache.get(src, build)
 
@@ -244,7 +245,7 @@ class SwinTransformerBlock(nn.Module):
         ops.rowgemm(A=x, a_mode=ops.A_F32_LN, M=M, K=C, lda=C, ln_w=pk["n1w"], ln_b=pk["n1b"], ln_eps=self.norm1.eps,
                     Wp=Wp, NT=NT, nchunks=nch, n_valid=nv, e_mode=ops.E_BF16, bias=bp, out=qkv, ldo=3 * C)
         att = torch.empty(M, C, device=x.device, dtype=ops.operand_dtype())
-        ops.window_attention(qkv, att, pk["qkv_b"], pk["tab"], B, H, W, C, self.num_heads, self.shift_size)
+        ops.window_attention(qkv, att, pk["qkv_b"], pk["tab"], B, H, W, C, self.num_heads, self.shift_size, pk["tabfrag"])
         Wp, bp, NT, nch, nv = pk["proj"]
         if tmp is None:
             tmp = torch.empty_like(out)

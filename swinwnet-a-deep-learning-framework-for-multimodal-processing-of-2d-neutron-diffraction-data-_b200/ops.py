@@ -126,10 +126,16 @@ def set_phase_profile(buf):
     _lib.check(_lib.load().swn_set_phase_profile(_ptr(buf)), "swn_set_phase_profile")
 
 
-def window_attention(qkv, out, qkv_bias, table, B, H, W, C, nH, shift=0):
-    with _Launch(qkv, out, qkv_bias, table) as st:
-        _lib.check(_lib.load().swn_window_attention(_ptr(qkv), _ptr(out), _ptr(qkv_bias), _ptr(table), B, H, W, C, nH, shift,
-                                                    st), "swn_window_attention")
+def window_attention(qkv, out, qkv_bias, table, B, H, W, C, nH, shift=0, bias_frags=None):
+    """bias_frags (shift 0 only): packing.rel_pos_bias_fragments(table, log2 e), cached by the caller — saves the per-CTA
+    rebuild of the bias images from the table"""
+    with _Launch(qkv, out, qkv_bias, table, bias_frags) as st:
+        if bias_frags is not None and shift == 0:
+            _lib.check(_lib.load().swn_window_attention_frags(_ptr(qkv), _ptr(out), _ptr(qkv_bias), _ptr(table), _ptr(bias_frags),
+                                                              B, H, W, C, nH, st), "swn_window_attention_frags")
+        else:
+            _lib.check(_lib.load().swn_window_attention(_ptr(qkv), _ptr(out), _ptr(qkv_bias), _ptr(table), B, H, W, C, nH, shift,
+                                                        st), "swn_window_attention")
     _count("window_attention")
 
 

@@ -111,6 +111,9 @@ for (L, C, nH, H, W) in SHAPES:
         bq, tab = torch.zeros(3 * C, device=DEV), torch.zeros(81, nH, device=DEV)
         ms = timeit(lambda: ops.window_attention(qkv, att, bq, tab, B, H, W, C, nH, 0))
         report("attn", M, C, ms, M * C * 8, 100.0 * M * C)
+        fr = packing.rel_pos_bias_fragments(tab, 1.4426950408889634).reshape(-1).contiguous()
+        ms = timeit(lambda: ops.window_attention(qkv, att, bq, tab, B, H, W, C, nH, 0, fr))
+        report("attnf", M, C, ms, M * C * 8, 100.0 * M * C)
     if "proj" in a.ops:
         att = torch.randn(M, C, device=DEV).to(OPD)
         Wo, bo = torch.randn(C, C, device=DEV) * C ** -0.5, torch.zeros(C, device=DEV)
