@@ -26,6 +26,9 @@ static void mlp_config(int C, int* HC, int* TR) {
   // C > 96: HC = 128 (full-rate N for GEMM1; at C = 384 TMEM then holds only ONE hidden accumulator next to the 384 Y
   // columns — measured 13 % faster than two 64-column accumulators: 0.60 -> 0.52 ms at M = 122 880)
   (void)hbase;
+#if SWN_MLP_TWO_CTA
+  if (C == 192) { *HC = 64; *TR = 96; return; }     // two co-resident CTAs per SM (mlp.cu)
+#endif
   if (C > 96 && Hd % 128 == 0) *HC = 128;
 #ifdef SWN_MLP96_HC
   else if (C == 96) *HC = SWN_MLP96_HC;

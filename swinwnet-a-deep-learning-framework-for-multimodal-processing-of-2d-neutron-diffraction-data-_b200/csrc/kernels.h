@@ -45,6 +45,9 @@ int launch_expand_warp(RowGemmParams p, int num_sms, cudaStream_t stream);
 int launch_rowgemm_persist(RowGemmParams p, int num_sms, cudaStream_t stream);
 
 // ---- mlp.cu ---------------------------------------------------------------------------------
+#ifndef SWN_MLP_TWO_CTA
+#define SWN_MLP_TWO_CTA 1   // C = 192: two co-resident CTAs per SM (HC = 64, TR = 96, one hidden accumulator); see mlp.cu
+#endif
 struct MlpParams {
   const float* x;    // [M, C] fp32 residual stream (input)
   float* out;        // [M, C] fp32 (may alias x)
