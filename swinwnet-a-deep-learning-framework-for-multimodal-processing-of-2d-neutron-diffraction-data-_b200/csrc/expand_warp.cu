@@ -1,4 +1,4 @@
-// PatchExpanding (+ crop) for the narrow decoder layers (K = 24 / 48 input channels; SwinWNet.py:397-424): Linear(K -> 2K,
+// PatchExpanding (+ crop) for the narrow decoder layers (K = 24 / 48 / 96 input channels; SwinWNet.py:397-424): Linear(K -> 2K,
 // no bias), pixel shuffle to the 2x grid, LayerNorm(K/2) — with the GEMM on warp-level mma.sync instead of a tcgen05 tile.
 // At K = 24 a 128 x 64-k tcgen05 tile is 62 % padding and the per-tile chain (rows -> smem A tile -> MMA -> TMEM -> two
 // round trips of the LayerNorm epilogue) ran at 2.3 TB/s.  Here a warp owns 32 consecutive token rows: they are loaded straight
@@ -32,10 +32,11 @@ template <int KT, int NT8>   // k-steps of 16 input channels, 8-column tiles per
 __global__ void __launch_bounds__(XW_THREADS, SWN_XW_MINB) expand_warp_kernel(const RowGemmParams p) {
   constexpr int KJ = 2 * KT;      // 8-column tiles of the (zero-padded) input row
   extern __shared__ __align__(16) uint8_t xw_smem[];
-  uint8_t* w_s = xw_smem;                                               // [4 chunks][NT rows][128 B] swizzled
-  float* lnw = reinterpret_cast<float*>(xw_smem + 4 * p.NT * 128);      // [NT8 * 8]
+  constexpr int KB = (KT + 3) / 4;                                      // 64-column k-blocks of the weight image
+  uint8_t* w_s = xw_smem;                                               // [4 chunks][KB][NT rows][128 B] swizzled
+  float* lnw = reinterpret_cast<float*>(xw_smem + 4 * KB * p.NT * 128); // [NT8 * 8]
   float* lnb = lnw + NT8 * 8;
-  for (int i = threadIdx.x; i < 4 * p.NT * 8; i += XW_THREADS)
+  for (int i = threadIdx.x; i < 4 * KB * p.NT * 8; i += XW_THREADS)
     reinterpret_cast<uint4*>(w_s)[i] = __ldg(reinterpret_cast<const uint4*>(p.Wp) + i);
   for (int i = threadIdx.x; i < NT8 * 8; i += XW_THREADS) {
     lnw[i] = i < p.n_valid ? p.ln2_w[i] : 0.f;
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(XW_THREADS, SWN_XW_MINB) expand_warp_kernel(co
     // ---- the four channel groups: chunk n = (i, j) = (n >> 1, n & 1) -> output pixel (2h + i, 2w + j) ----
 #pragma unroll 1
     for (int n = 0; n < 4; ++n) {
-      const uint8_t* wc = w_s + n * p.NT * 128;
+      const uint8_t* wc = w_s + n * KB * p.NT * 128;
       float acc[2][NT8][4];
 #pragma unroll
       for (int nt = 0; nt < NT8; ++nt) {
@@ -89,8 +90,9 @@ __global__ void __launch_bounds__(XW_THREADS, SWN_XW_MINB) expand_warp_kernel(co
 #pragma unroll
         for (int kt = 0; kt < KT; ++kt) {
           const uint32_t r = 8 * nt + g;
-          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wc + r * 128 + ((((uint32_t)(2 * kt)) ^ r) & 7u) * 16 + 4 * t);
-          const uint32_t b1 = *reinterpret_cast<const uint32_t*>(wc + r * 128 + ((((uint32_t)(2 * kt + 1)) ^ r) & 7u) * 16 + 4 * t);
+          const uint8_t* wb = wc + (kt >> 2) * p.NT * 128 + r * 128 + 4 * t;       // k-block kt / 4, 16-byte chunks 2 (kt % 4), + 1
+          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wb + ((((uint32_t)(2 * (kt & 3))) ^ r) & 7u) * 16);
+          const uint32_t b1 = *reinterpret_cast<const uint32_t*>(wb + ((((uint32_t)(2 * (kt & 3) + 1)) ^ r) & 7u) * 16);
           xw_mma(acc[0][nt], a[0][kt], b0, b1);
           xw_mma(acc[1][nt], a[1][kt], b0, b1);
         }
@@ -137,21 +139,23 @@ int launch_expand_warp(RowGemmParams p, int num_sms, cudaStream_t stream) {
 #ifndef SWN_EXPAND_WARP
 #define SWN_EXPAND_WARP 1
 #endif
-  if (!SWN_EXPAND_WARP || p.e_mode != E_EXPAND || p.a_mode != A_F32 || p.K > 48 || p.K % 4 != 0 || p.nchunks != 4 || p.n_valid % 4 != 0 ||
-      (p.NT != 16 && p.NT != 32) || p.lda % 2 != 0 || p.ldo % 2 != 0)
+  if (!SWN_EXPAND_WARP || p.e_mode != E_EXPAND || p.a_mode != A_F32 || p.K > 96 || p.K % 4 != 0 || p.nchunks != 4 || p.n_valid % 4 != 0 ||
+      (p.NT != 16 && p.NT != 32 && p.NT != 48) || p.lda % 2 != 0 || p.ldo % 2 != 0)
     return -1;
   const int KT = (p.K + 15) / 16;
-  if (KT > 3 || (KT == 3 && p.NT != 32)) return -1;
-  const size_t smem = (size_t)4 * p.NT * 128 + 2 * p.NT * 4;
+  if ((p.NT == 16 && KT > 2) || (p.NT == 32 && KT > 3) || (p.NT == 48 && KT != 6)) return -1;
+  const size_t smem = (size_t)4 * ((KT + 3) / 4) * p.NT * 128 + 2 * p.NT * 4;
   auto go = [&](auto kern) -> int {
     const long long ngroups = ((long long)p.M + 31) / 32;
     long long grid = (long long)num_sms * SWN_XW_MINB;
     const long long need = (ngroups + XW_THREADS / 32 - 1) / (XW_THREADS / 32);
     if (grid > need) grid = need;
+    SWN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)grid, XW_THREADS, smem, stream>>>(p);
     SWN_CUDA(cudaGetLastError());
     return 0;
   };
+  if (p.NT == 48) return go(expand_warp_kernel<6, 6>);
   if (p.NT == 16) return KT == 1 ? go(expand_warp_kernel<1, 2>) : go(expand_warp_kernel<2, 2>);
   return KT == 1 ? go(expand_warp_kernel<1, 4>) : (KT == 2 ? go(expand_warp_kernel<2, 4>) : go(expand_warp_kernel<3, 4>));
 }
