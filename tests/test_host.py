@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_mlp_config_host_call_and_errors():
     lib = _lib.load()
-    for C, exp in ((12, (48, 16)), (24, (96, 32)), (48, (64, 48)), (96, (96, 96)), (192, (128, 192)), (384, (128, 128))):
+    for C, exp in ((12, (48, 16)), (24, (96, 32)), (48, (64, 48)), (96, (96, 96)), (192, (64, 96)), (384, (128, 128))):
         hc, tr = ctypes.c_int(), ctypes.c_int()
         assert lib.swn_mlp_config(C, ctypes.byref(hc), ctypes.byref(tr)) == 0
         assert (hc.value, tr.value) == exp, (C, hc.value, tr.value)
