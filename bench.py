@@ -546,5 +546,26 @@ def main():
         sys.exit(rc)
 
 
+class _JsonOnlyStdout:
+    """Everything libraries write to file descriptor 1 while the benchmark runs (NCCL prints its version banner there) goes to
+    stderr; only the lines this script print()s — the JSON line — reach the real stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._real = os.dup(1)
+        os.dup2(2, 1)
+        sys.stdout = os.fdopen(os.dup(self._real), "w")
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        sys.stdout.close()
+        os.dup2(self._real, 1)
+        os.close(self._real)
+        sys.stdout = sys.__stdout__
+        return False
+
+
 if __name__ == "__main__":
-    main()
+    with _JsonOnlyStdout():
+        main()
